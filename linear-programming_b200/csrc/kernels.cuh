@@ -1,0 +1,414 @@
+// kernels.cuh -- sm_100a kernels of the dense tableau simplex iteration.
+//
+// One simplex iteration = the reference's loop body, src/simplex.lisp:455-460:
+//   k_enter   find-entering-column  :362-379   reduced-cost row scan, (value,index) argmin
+//   k_ratio   find-pivoting-row     :382-389   strided column gather + ratio argmin; also
+//                                              snapshots the pivot column a[:,j] (n-pivot-row
+//                                              reads each a[r,j] before row r changes, :353)
+//   k_cand    n-pivot-row part 1    :344-348   candidate pivot row / pivot element
+//   k_winner  (sharded only)                   pick the global leaving row from all ranks
+//   k_pivot   n-pivot-row part 2    :349-358   rank-1 update, the HBM-bound hot kernel
+//
+// Arithmetic contract (bit-identical to the reference's double-float path and to
+// oracle/simplex_oracle.c): __ddiv_rn for the row scale and the ratios, __dmul_rn then
+// __dsub_rn for the update (never contracted into an FMA), strict compares with lowest-index
+// tie-breaks.  Every kernel returns at once when the device status word is not RUNNING, so
+// the host can enqueue iterations ahead of knowing whether the solve has finished.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200lp {
+
+constexpr int ST_RUNNING = 100;          // device-only; public codes are in b200lp.h
+constexpr int ST_OPTIMAL = 0;
+constexpr int ST_UNBOUNDED = 1;
+constexpr int ST_ITERATION_LIMIT = 3;
+
+constexpr int kEnterThreads = 1024;
+constexpr int kRatioThreads = 256;
+constexpr int kPivotThreads = 256;
+constexpr int kCandHdr = 4;              // doubles in front of a candidate row (32 B)
+
+// Device-resident loop state; one per shard.
+struct alignas(16) DevState {
+    int status;               // ST_RUNNING or a final code
+    int j;                    // entering column of the current iteration
+    int p;                    // leaving row (GLOBAL row index) of the current iteration
+    int winner;               // rank whose candidate row won (0 when unsharded)
+    long long iters;          // pivots completed
+    long long max_iters;      // 0 = unlimited
+    double q;                 // winning ratio
+    unsigned int ticket;      // last-block ticket of k_ratio
+    int forced_row;           // >= 0: b200lp_pivot / clean-up pivots skip the ratio argmin
+};
+
+// Header in front of each candidate pivot row (exchanged between ranks when sharded).
+struct alignas(16) CandHdr {
+    double q;                 // b_r / a[r,j]
+    long long key;            // tie-break key: global row (reference rule) or basis[r] (Bland)
+    long long row;            // global row index, -1 = this rank has no eligible row
+    long long pad;
+};
+static_assert(sizeof(CandHdr) == kCandHdr * sizeof(double), "header size");
+
+struct Cand { double q; int key; int row; };
+
+// (q, key) lexicographic minimum; row < 0 marks "no candidate".  Reproduces the sequential
+// `finding i minimizing` rule: strict <, first index wins (key == global row for rule 0).
+__device__ __forceinline__ Cand cand_min(const Cand a, const Cand b)
+{
+    if (b.row < 0) return a;
+    if (a.row < 0) return b;
+    if (b.q < a.q || (b.q == a.q && b.key < a.key)) return b;
+    return a;
+}
+
+__device__ __forceinline__ Cand cand_shfl_xor(const Cand c, int lane_mask)
+{
+    Cand o;
+    o.q = __shfl_xor_sync(0xffffffffu, c.q, lane_mask);
+    o.key = __shfl_xor_sync(0xffffffffu, c.key, lane_mask);
+    o.row = __shfl_xor_sync(0xffffffffu, c.row, lane_mask);
+    return o;
+}
+
+__device__ __forceinline__ Cand cand_warp_min(Cand c)
+{
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) c = cand_min(c, cand_shfl_xor(c, s));
+    return c;
+}
+
+template <int THREADS>
+__device__ __forceinline__ Cand cand_block_min(Cand c, Cand *smem /* THREADS/32 */)
+{
+    c = cand_warp_min(c);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) smem[warp] = c;
+    __syncthreads();
+    if (warp == 0) {
+        Cand d;
+        d.q = 0.0; d.key = 0; d.row = -1;
+        if (lane < THREADS / 32) d = smem[lane];
+        d = cand_warp_min(d);
+        if (lane == 0) smem[0] = d;
+    }
+    __syncthreads();
+    return smem[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// k_enter: find-entering-column (src/simplex.lisp:362-379).  One CTA scans the objective row.
+// max problem: first argmin, accept iff value < -(tol/8)eps; min problem: first argmax, accept
+// iff value > +(tol/8)eps -- folded into one argmin over key = is_max ? v : -v (negation is
+// exact and order reversing).  Bland: lowest index whose key passes the same threshold.
+// Also enforces the iteration cap (build extension) once an entering column exists.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEnterThreads)
+k_enter(const double *__restrict__ obj, int nv, int is_max, double thr, int rule, DevState *st)
+{
+    if (st->status != ST_RUNNING) return;
+    __shared__ Cand red[kEnterThreads / 32];
+    Cand best;
+    best.q = 0.0; best.key = 0; best.row = -1;
+    if (rule == 0) {
+        for (int i = threadIdx.x; i < nv; i += kEnterThreads) {
+            const double v = obj[i];
+            const double k = is_max ? v : -v;
+            if (best.row < 0 || k < best.q) { best.q = k; best.key = i; best.row = i; }
+        }
+    } else {
+        for (int i = threadIdx.x; i < nv; i += kEnterThreads) {
+            const double v = obj[i];
+            const double k = is_max ? v : -v;
+            if (k < 0.0 - thr) { best.q = 0.0; best.key = i; best.row = i; break; }
+        }
+    }
+    best = cand_block_min<kEnterThreads>(best, red);
+    if (threadIdx.x == 0) {
+        const bool accept = (best.row >= 0) && (rule != 0 || best.q < 0.0 - thr);
+        if (!accept) {
+            st->status = ST_OPTIMAL;
+            st->j = -1;
+        } else if (st->max_iters > 0 && st->iters >= st->max_iters) {
+            st->status = ST_ITERATION_LIMIT;
+            st->j = best.row;
+        } else {
+            st->j = best.row;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_ratio: find-pivoting-row (src/simplex.lisp:382-389) over this shard's rows, fused with the
+// pivot-column snapshot colbuf[i] = a[i,j] for every local row including the objective replica.
+// Eligible rows: a[i,j] > (tol/2)eps; ratio = rhs_i / a[i,j] (true division, no clamp).
+// Multi-CTA; the last CTA to finish (ticket) reduces the per-CTA partials and publishes the
+// shard's candidate.  Unsharded (world == 1) it also finalises the iteration: leaving row,
+// UNBOUNDED status, pivot trace.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRatioThreads)
+k_ratio(const double *__restrict__ tab, int64_t ld, int m_local, int R_local, int rhs_col,
+        const int32_t *__restrict__ basis, int row0, double thr, int rule, int world,
+        double *__restrict__ colbuf, DevState *st, Cand *__restrict__ partials,
+        CandHdr *__restrict__ hdr, int2 *__restrict__ trace, int trace_cap)
+{
+    if (st->status != ST_RUNNING) return;
+    __shared__ Cand red[kRatioThreads / 32];
+    __shared__ bool is_last;
+    const int j = st->j;
+    const int forced = st->forced_row;
+    const int i = blockIdx.x * kRatioThreads + threadIdx.x;
+    Cand c;
+    c.q = 0.0; c.key = 0; c.row = -1;
+    if (i < R_local) {
+        const double a = tab[(int64_t)i * ld + j];
+        colbuf[i] = a;
+        if (i < m_local) {
+            if (forced >= 0) {
+                if (row0 + i == forced) { c.q = 0.0; c.key = 0; c.row = forced; }
+            } else if (0.0 + thr < a) {
+                c.q = __ddiv_rn(tab[(int64_t)i * ld + rhs_col], a);
+                c.key = rule ? basis[i] : row0 + i;
+                c.row = row0 + i;
+            }
+        }
+    }
+    c = cand_block_min<kRatioThreads>(c, red);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = c;
+        __threadfence();
+        const unsigned int t = atomicAdd(&st->ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    Cand d;
+    d.q = 0.0; d.key = 0; d.row = -1;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += kRatioThreads) {
+        // volatile: written by other CTAs of this launch
+        const volatile Cand *vp = partials + b;
+        Cand o;
+        o.q = vp->q; o.key = vp->key; o.row = vp->row;
+        d = cand_min(d, o);
+    }
+    __syncthreads();
+    d = cand_block_min<kRatioThreads>(d, red);
+    if (threadIdx.x == 0) {
+        st->ticket = 0;
+        hdr->q = d.q; hdr->key = d.key; hdr->row = d.row; hdr->pad = 0;
+        if (world == 1) {
+            if (d.row < 0) {
+                st->status = ST_UNBOUNDED;
+                st->p = -1;
+            } else {
+                st->p = d.row;
+                st->q = d.q;
+                st->winner = 0;
+                if (trace && st->iters < trace_cap) trace[st->iters] = make_int2(j, d.row);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_cand: n-pivot-row part 1 (src/simplex.lisp:344-348): this shard's candidate row divided by
+// its pivot element, written behind the header; pad columns [C, ld) are zeroed so the update
+// may run over whole 16-byte vectors.  A shard without an eligible row writes nothing.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_cand(const double *__restrict__ tab, int64_t ld, int C, int row0, const DevState *st,
+       const CandHdr *__restrict__ hdr, double *__restrict__ cand_row)
+{
+    if (st->status != ST_RUNNING) return;
+    const long long row = hdr->row;
+    if (row < 0) return;
+    const double *src = tab + (row - row0) * ld;
+    const double s = src[st->j];
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < (int)ld; c += gridDim.x * blockDim.x)
+        cand_row[c] = (c < C) ? __ddiv_rn(src[c], s) : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_winner (sharded only): after the all-gather every rank holds all candidates; each picks the
+// same (ratio, key) lexicographic minimum, i.e. the row the unsharded scan would have picked.
+// ------------------------------------------------------------------------------------------
+__global__ void k_winner(const double *__restrict__ gathered, int64_t stride, int world,
+                         DevState *st, int2 *__restrict__ trace, int trace_cap)
+{
+    if (st->status != ST_RUNNING) return;
+    if (threadIdx.x != 0) return;
+    Cand best;
+    best.q = 0.0; best.key = 0; best.row = -1;
+    int w = -1;
+    for (int g = 0; g < world; ++g) {
+        const CandHdr *h = reinterpret_cast<const CandHdr *>(gathered + g * stride);
+        Cand c;
+        c.q = h->q; c.key = (int)h->key; c.row = (int)h->row;
+        const Cand nb = cand_min(best, c);
+        if (nb.row != best.row) { best = nb; w = g; }
+    }
+    if (best.row < 0) {
+        st->status = ST_UNBOUNDED;
+        st->p = -1;
+    } else {
+        st->p = best.row;
+        st->q = best.q;
+        st->winner = w;
+        if (trace && st->iters < trace_cap) trace[st->iters] = make_int2(st->j, best.row);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_pivot: n-pivot-row part 2 (src/simplex.lisp:349-358), the bandwidth-bound hot kernel.
+//   row p            <- scaled pivot row
+//   every other row r <- a[r,:] - colbuf[r] * prow[:]   (objective replica included)
+// In place; each element is read once and written once: 16*R*C algorithmic bytes.
+// Tiling: CTA = TR rows x (256 threads * VEC double2) columns; every thread keeps its slice of
+// the pivot row in registers and streams UNROLL rows of 16-byte loads before the stores.
+// ------------------------------------------------------------------------------------------
+template <bool STREAM>
+__device__ __forceinline__ double2 ld_tab(const double2 *p)
+{
+    if (STREAM) return __ldcs(p);
+    return *p;
+}
+template <bool STREAM>
+__device__ __forceinline__ void st_tab(double2 *p, const double2 v)
+{
+    if (STREAM) __stcs(p, v);
+    else *p = v;
+}
+
+template <int TR, int UNROLL, int VEC, bool STREAM>
+__global__ void __launch_bounds__(kPivotThreads)
+k_pivot(double *__restrict__ tab, int64_t ld, int m_local, int R_local, int row0,
+        const double *__restrict__ colbuf, const double *__restrict__ cand_base, int64_t cand_stride,
+        int32_t *__restrict__ basis, DevState *st)
+{
+    if (st->status != ST_RUNNING) return;
+    __shared__ double s_col[TR];
+    const int ldv = (int)(ld >> 1);                       // row length in double2
+    const int r_begin = blockIdx.y * TR;
+    const int r_end = min(R_local, r_begin + TR);
+    for (int t = threadIdx.x; t < TR; t += kPivotThreads)
+        s_col[t] = (r_begin + t < r_end) ? colbuf[r_begin + t] : 0.0;
+    const int p_global = st->p;
+    const int p_rel = p_global - row0;
+    const int p_local = (p_rel >= 0 && p_rel < m_local) ? p_rel : -1;
+    const double2 *prow2 =
+        reinterpret_cast<const double2 *>(cand_base + (int64_t)st->winner * cand_stride + kCandHdr);
+    int cv[VEC];
+    double2 pr[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        cv[v] = (blockIdx.x * VEC + v) * kPivotThreads + threadIdx.x;
+        pr[v] = (cv[v] < ldv) ? prow2[cv[v]] : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    double2 *tab2 = reinterpret_cast<double2 *>(tab);
+    for (int r = r_begin; r < r_end; r += UNROLL) {
+        double2 a[UNROLL][VEC];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+                if (r + u < r_end && cv[v] < ldv)
+                    a[u][v] = ld_tab<STREAM>(tab2 + (int64_t)(r + u) * ldv + cv[v]);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if (r + u < r_end) {
+                const double t = s_col[r + u - r_begin];
+                const bool is_p = (r + u == p_local);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    if (cv[v] < ldv) {
+                        double2 o;
+                        o.x = __dsub_rn(a[u][v].x, __dmul_rn(t, pr[v].x));
+                        o.y = __dsub_rn(a[u][v].y, __dmul_rn(t, pr[v].y));
+                        if (is_p) o = pr[v];
+                        st_tab<STREAM>(tab2 + (int64_t)(r + u) * ldv + cv[v], o);
+                    }
+                }
+            }
+        }
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        if (p_local >= 0) basis[p_local] = st->j;         // (setf (aref basis p) j) :358
+        st->iters += 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Small helpers for the boundary: gather the RHS column into a contiguous buffer (what
+// tableau-variable reads, src/simplex.lisp:81-107) and the two-phase transition pieces.
+// ------------------------------------------------------------------------------------------
+__global__ void k_gather_col(const double *__restrict__ tab, int64_t ld, int R_local, int col,
+                             double *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < R_local) out[i] = tab[(int64_t)i * ld + col];
+}
+
+__global__ void k_zero_pad(double *__restrict__ tab, int64_t ld, int R_local, int C)
+{
+    const int pad = (int)ld - C;
+    const int64_t n = (int64_t)R_local * pad;
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n;
+         k += (int64_t)gridDim.x * blockDim.x)
+        tab[(k / pad) * ld + C + (k % pad)] = 0.0;
+}
+
+// Phase-1 -> phase-2 coefficient copy (src/simplex.lisp:437-441): constraint rows only;
+// main[r, 0..nv) = art[r, 0..nv); main[r, nv] = art[r, art_nv].
+__global__ void k_copy_art_to_main(const double *__restrict__ art, int64_t ld_art, int art_nv,
+                                   double *__restrict__ mtab, int64_t ld, int nv, int m)
+{
+    for (int r = blockIdx.y; r < m; r += gridDim.y)
+        for (int c = blockIdx.x * blockDim.x + threadIdx.x; c <= nv; c += gridDim.x * blockDim.x)
+            mtab[(int64_t)r * ld + c] = art[(int64_t)r * ld_art + (c < nv ? c : art_nv)];
+}
+
+// Objective re-pricing (src/simplex.lisp:444-451): for i = 0..m-1 in order, scale_i =
+// obj[basis_i] (the basis columns are exact unit vectors, so the sequential read equals the
+// snapshot taken here), obj[c] -= scale_i * main[i,c] when scale_i /= 0.  One thread per column
+// keeps the row order, hence the rounding sequence, of the reference.
+__global__ void k_reprice_scales(const double *__restrict__ obj, const int32_t *__restrict__ basis,
+                                 int m, double *__restrict__ scales)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) scales[i] = obj[basis[i]];
+}
+
+__global__ void k_reprice(double *__restrict__ mtab, int64_t ld, int m, int nv,
+                          const double *__restrict__ scales)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > nv) return;
+    double acc = mtab[(int64_t)m * ld + c];
+    for (int i = 0; i < m; ++i) {
+        const double s = scales[i];
+        if (s != 0.0) acc = __dsub_rn(acc, __dmul_rn(s, mtab[(int64_t)i * ld + c]));
+    }
+    mtab[(int64_t)m * ld + c] = acc;
+}
+
+// First non-basic column j < nv with an exactly non-zero entry in `row` (src/simplex.lisp:426-431);
+// is_basic[] marks columns currently in the basis.  Single CTA; result -1 when none.
+__global__ void k_first_nonzero_nonbasic(const double *__restrict__ row, int nv,
+                                         const unsigned char *__restrict__ is_basic, int *out)
+{
+    __shared__ int best;
+    if (threadIdx.x == 0) best = 0x7fffffff;
+    __syncthreads();
+    int mine = 0x7fffffff;
+    for (int c = threadIdx.x; c < nv; c += blockDim.x)
+        if (row[c] != 0.0 && !is_basic[c]) { mine = c; break; }
+    atomicMin(&best, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) *out = (best == 0x7fffffff) ? -1 : best;
+}
+
+} // namespace b200lp

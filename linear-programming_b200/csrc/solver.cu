@@ -1,0 +1,986 @@
+// solver.cu -- host side of libb200lp.so: the device-resident simplex loop and the C ABI
+// declared in include/b200lp.h.
+//
+// Replaces the reference's n-solve-tableau (src/simplex.lisp:399-461).  The tableau lives in
+// HBM for the whole solve; the host only enqueues iterations (every kernel returns at once when
+// the device status word says the solve is over) and polls that word every `poll_interval`
+// pivots, one batch behind the enqueue front so the GPU queue never drains.
+//
+// Sharding: contiguous row blocks (b200lp_partition), objective row replicated on every shard;
+// per iteration one NCCL all-gather carries each shard's (ratio, key, row | scaled candidate
+// row), after which every shard picks the same winner.  A shard is one GPU: either one per
+// process (b200lp_create_sharded, torchrun style) or several in this process (opts.ndev > 1).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/b200lp.h"
+#include "kernels.cuh"
+#include "nccl_dyn.h"
+
+namespace b200lp {
+
+// CL double-float-epsilon (SBCL): 2^-53 (1 + 2^-52); src/utils.lisp:92,107 scale it by `factor`.
+static constexpr double kClEps = 0x1.0000000000001p-53;
+
+static thread_local std::string g_last_error;
+static NcclApi g_nccl;
+static std::mutex g_nccl_mu;
+
+static int fail(int code, const char *what, const char *detail)
+{
+    g_last_error = std::string(what) + ": " + (detail ? detail : "");
+    return code;
+}
+
+#define CU_TRY(expr)                                                                     \
+    do {                                                                                 \
+        cudaError_t e__ = (expr);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            (void)cudaGetLastError();                                                    \
+            return fail(e__ == cudaErrorMemoryAllocation ? B200LP_ERR_OUT_OF_MEMORY      \
+                                                         : B200LP_ERR_CUDA,              \
+                        #expr, cudaGetErrorString(e__));                                 \
+        }                                                                                \
+    } while (0)
+
+#define NCCL_TRY(expr)                                                                   \
+    do {                                                                                 \
+        ncclResult_t r__ = (expr);                                                       \
+        if (r__ != ncclSuccess)                                                          \
+            return fail(B200LP_ERR_NCCL, #expr, g_nccl.GetErrorString(r__));             \
+    } while (0)
+
+#define RC_TRY(expr)                                                                     \
+    do {                                                                                 \
+        int rc__ = (expr);                                                               \
+        if (rc__ != B200LP_OK) return rc__;                                              \
+    } while (0)
+
+static double now_ms()
+{
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+static int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+struct Shard {
+    int device = 0;
+    int rank = 0;               // global rank of this shard
+    int64_t row0 = 0;           // first global constraint row owned
+    int m_local = 0;            // constraint rows owned
+    int R_local = 0;            // m_local + 1 (objective replica last)
+    int64_t ld = 0;             // device leading dimension (multiple of 16 doubles)
+    cudaStream_t stream = nullptr;
+    double *tab = nullptr;
+    int32_t *basis = nullptr;
+    double *colbuf = nullptr;
+    double *cand = nullptr;     // CandHdr + ld doubles
+    double *gathered = nullptr; // world * (kCandHdr + ld) doubles (sharded only)
+    double *colout = nullptr;   // R_local doubles, RHS gather
+    DevState *st = nullptr;
+    Cand *partials = nullptr;
+    int2 *trace = nullptr;
+    DevState *h_st = nullptr;   // pinned, 2 slots
+    int2 *h_trace = nullptr;
+    ncclComm_t comm = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_poll[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_pivot; // pairs
+    int ratio_blocks = 0;
+};
+
+} // namespace b200lp
+
+using namespace b200lp;
+
+struct b200lp_solver {
+    b200lp_opts opts;
+    int64_t R = 0, C = 0, m = 0;
+    int is_max = 1;
+    double tol = 1024.0, thr_enter = 0, thr_pivot = 0, thr_feas = 0;
+    int world = 1;
+    bool multiprocess = false;
+    std::vector<Shard> shards;
+    std::mutex mu;
+    long long iters_done = 0;   // host mirror of DevState::iters
+    int64_t kernel_launches = 0;
+    int64_t pivot_launches_timed = 0;
+    size_t ev_used = 0;
+};
+
+namespace b200lp {
+
+static void fill_thresholds(b200lp_solver *s)
+{
+    s->tol = s->opts.fp_tolerance_factor > 0 ? s->opts.fp_tolerance_factor : 1024.0;
+    b200lp_thresholds(s->tol, &s->thr_enter, &s->thr_pivot, &s->thr_feas);
+}
+
+static int alloc_shard(b200lp_solver *s, Shard &sh)
+{
+    CU_TRY(cudaSetDevice(sh.device));
+    CU_TRY(cudaStreamCreateWithFlags(&sh.stream, cudaStreamNonBlocking));
+    sh.ld = round_up(s->C, 16);
+    const int64_t stride = kCandHdr + sh.ld;
+    CU_TRY(cudaMalloc(&sh.tab, sizeof(double) * sh.ld * sh.R_local));
+    CU_TRY(cudaMalloc(&sh.basis, sizeof(int32_t) * std::max(1, sh.m_local)));
+    CU_TRY(cudaMalloc(&sh.colbuf, sizeof(double) * sh.R_local));
+    CU_TRY(cudaMalloc(&sh.colout, sizeof(double) * sh.R_local));
+    CU_TRY(cudaMalloc(&sh.cand, sizeof(double) * stride));
+    CU_TRY(cudaMemsetAsync(sh.cand, 0, sizeof(double) * stride, sh.stream));
+    if (s->world > 1) {
+        CU_TRY(cudaMalloc(&sh.gathered, sizeof(double) * stride * s->world));
+        CU_TRY(cudaMemsetAsync(sh.gathered, 0, sizeof(double) * stride * s->world, sh.stream));
+    }
+    sh.ratio_blocks = (sh.R_local + kRatioThreads - 1) / kRatioThreads;
+    CU_TRY(cudaMalloc(&sh.partials, sizeof(Cand) * sh.ratio_blocks));
+    CU_TRY(cudaMalloc(&sh.st, sizeof(DevState)));
+    CU_TRY(cudaMemsetAsync(sh.st, 0, sizeof(DevState), sh.stream));
+    CU_TRY(cudaMallocHost(&sh.h_st, 2 * sizeof(DevState)));
+    const int tc = s->opts.trace_capacity;
+    if (tc > 0) {
+        CU_TRY(cudaMalloc(&sh.trace, sizeof(int2) * tc));
+        CU_TRY(cudaMallocHost(&sh.h_trace, sizeof(int2) * tc));
+    }
+    CU_TRY(cudaEventCreate(&sh.ev_begin));
+    CU_TRY(cudaEventCreate(&sh.ev_end));
+    CU_TRY(cudaEventCreateWithFlags(&sh.ev_poll[0], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&sh.ev_poll[1], cudaEventDisableTiming));
+    CU_TRY(cudaStreamSynchronize(sh.stream));
+    return B200LP_OK;
+}
+
+static void free_shard(Shard &sh)
+{
+    cudaSetDevice(sh.device);
+    if (sh.stream) cudaStreamSynchronize(sh.stream);
+    if (sh.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(sh.comm);
+    cudaFree(sh.tab); cudaFree(sh.basis); cudaFree(sh.colbuf); cudaFree(sh.colout);
+    cudaFree(sh.cand); cudaFree(sh.gathered); cudaFree(sh.partials); cudaFree(sh.st);
+    cudaFree(sh.trace);
+    if (sh.h_st) cudaFreeHost(sh.h_st);
+    if (sh.h_trace) cudaFreeHost(sh.h_trace);
+    for (cudaEvent_t e : sh.ev_pivot) cudaEventDestroy(e);
+    if (sh.ev_begin) cudaEventDestroy(sh.ev_begin);
+    if (sh.ev_end) cudaEventDestroy(sh.ev_end);
+    for (int k = 0; k < 2; ++k) if (sh.ev_poll[k]) cudaEventDestroy(sh.ev_poll[k]);
+    if (sh.stream) cudaStreamDestroy(sh.stream);
+    sh = Shard();
+}
+
+// Write the loop-control words; iters is kept from the host mirror.
+static int push_state(b200lp_solver *s, int status, long long max_iters, int j, int forced_row)
+{
+    for (Shard &sh : s->shards) {
+        CU_TRY(cudaSetDevice(sh.device));
+        DevState *h = &sh.h_st[0];
+        std::memset(h, 0, sizeof(DevState));
+        h->status = status;
+        h->j = j;
+        h->p = -1;
+        h->winner = 0;
+        h->iters = s->iters_done;
+        h->max_iters = max_iters;
+        h->forced_row = forced_row;
+        CU_TRY(cudaMemcpyAsync(sh.st, h, sizeof(DevState), cudaMemcpyHostToDevice, sh.stream));
+        // the pinned slot is reused by polls: make sure the copy has consumed it
+        CU_TRY(cudaStreamSynchronize(sh.stream));
+    }
+    return B200LP_OK;
+}
+
+static int pull_state(b200lp_solver *s, DevState *out)
+{
+    Shard &sh = s->shards[0];
+    CU_TRY(cudaSetDevice(sh.device));
+    CU_TRY(cudaMemcpyAsync(&sh.h_st[0], sh.st, sizeof(DevState), cudaMemcpyDeviceToHost, sh.stream));
+    CU_TRY(cudaStreamSynchronize(sh.stream));
+    *out = sh.h_st[0];
+    // the other shards finish the same kernels; wait so callers may touch their memory
+    for (size_t k = 1; k < s->shards.size(); ++k) {
+        CU_TRY(cudaSetDevice(s->shards[k].device));
+        CU_TRY(cudaStreamSynchronize(s->shards[k].stream));
+    }
+    return B200LP_OK;
+}
+
+// ---- kernel launches -------------------------------------------------------------------------
+static void launch_enter(b200lp_solver *s, Shard &sh)
+{
+    const double *obj = sh.tab + (int64_t)sh.m_local * sh.ld;
+    k_enter<<<1, kEnterThreads, 0, sh.stream>>>(obj, (int)(s->C - 1), s->is_max, s->thr_enter,
+                                                s->opts.pivot_rule, sh.st);
+    s->kernel_launches++;
+}
+
+static void launch_ratio(b200lp_solver *s, Shard &sh, bool with_trace)
+{
+    k_ratio<<<sh.ratio_blocks, kRatioThreads, 0, sh.stream>>>(
+        sh.tab, sh.ld, sh.m_local, sh.R_local, (int)(s->C - 1), sh.basis, (int)sh.row0,
+        s->thr_pivot, s->opts.pivot_rule, s->world, sh.colbuf, sh.st, sh.partials,
+        reinterpret_cast<CandHdr *>(sh.cand), with_trace ? sh.trace : nullptr,
+        s->opts.trace_capacity);
+    s->kernel_launches++;
+}
+
+static void launch_cand(b200lp_solver *s, Shard &sh)
+{
+    const int blocks = (int)std::min<int64_t>((sh.ld + 255) / 256, 148);
+    k_cand<<<blocks, 256, 0, sh.stream>>>(sh.tab, sh.ld, (int)s->C, (int)sh.row0, sh.st,
+                                          reinterpret_cast<const CandHdr *>(sh.cand),
+                                          sh.cand + kCandHdr);
+    s->kernel_launches++;
+}
+
+static void launch_winner(b200lp_solver *s, Shard &sh, bool with_trace)
+{
+    k_winner<<<1, 32, 0, sh.stream>>>(sh.gathered, kCandHdr + sh.ld, s->world, sh.st,
+                                      with_trace ? sh.trace : nullptr, s->opts.trace_capacity);
+    s->kernel_launches++;
+}
+
+template <int TR, int UNROLL, int VEC, bool STREAM>
+static void launch_pivot_t(b200lp_solver *s, Shard &sh)
+{
+    const int ldv = (int)(sh.ld / 2);
+    dim3 grid((ldv + kPivotThreads * VEC - 1) / (kPivotThreads * VEC), (sh.R_local + TR - 1) / TR);
+    const double *cand_base = s->world > 1 ? sh.gathered : sh.cand;
+    k_pivot<TR, UNROLL, VEC, STREAM><<<grid, kPivotThreads, 0, sh.stream>>>(
+        sh.tab, sh.ld, sh.m_local, sh.R_local, (int)sh.row0, sh.colbuf, cand_base,
+        kCandHdr + sh.ld, sh.basis, sh.st);
+}
+
+static void launch_pivot(b200lp_solver *s, Shard &sh)
+{
+    int v = s->opts.pivot_variant;
+    if (v == 0) {
+        // Tableaus that fit the 126 MB L2 keep default caching; larger ones stream.
+        const double bytes = 8.0 * (double)sh.ld * sh.R_local;
+        v = bytes > 96e6 ? 1 : 2;
+    }
+    switch (v) {
+    default:
+    case 1: launch_pivot_t<64, 8, 1, true>(s, sh); break;
+    case 2: launch_pivot_t<64, 8, 1, false>(s, sh); break;
+    case 3: launch_pivot_t<128, 8, 1, true>(s, sh); break;
+    case 4: launch_pivot_t<64, 4, 2, true>(s, sh); break;
+    case 5: launch_pivot_t<32, 8, 1, true>(s, sh); break;
+    case 6: launch_pivot_t<64, 16, 1, true>(s, sh); break;
+    case 7: launch_pivot_t<128, 8, 2, true>(s, sh); break;
+    case 8: launch_pivot_t<64, 4, 1, true>(s, sh); break;
+    case 9: launch_pivot_t<128, 16, 1, false>(s, sh); break;
+    }
+    s->kernel_launches++;
+}
+
+static int exchange(b200lp_solver *s)
+{
+    if (s->world == 1) return B200LP_OK;
+    const size_t bytes = sizeof(double) * (kCandHdr + s->shards[0].ld);
+    if (s->shards.size() > 1) NCCL_TRY(g_nccl.GroupStart());
+    for (Shard &sh : s->shards) {
+        if (s->shards.size() > 1) cudaSetDevice(sh.device);
+        NCCL_TRY(g_nccl.AllGather(sh.cand, sh.gathered, bytes, ncclChar, sh.comm, sh.stream));
+    }
+    if (s->shards.size() > 1) NCCL_TRY(g_nccl.GroupEnd());
+    return B200LP_OK;
+}
+
+// One full simplex iteration on every local shard.  `do_enter` is false for forced pivots.
+static int enqueue_iteration(b200lp_solver *s, bool do_enter, bool with_trace, bool time_pivot)
+{
+    const bool multi = s->shards.size() > 1;
+    for (Shard &sh : s->shards) {
+        if (multi) CU_TRY(cudaSetDevice(sh.device));
+        if (do_enter) launch_enter(s, sh);
+        launch_ratio(s, sh, with_trace);
+        launch_cand(s, sh);
+    }
+    if (s->world > 1) {
+        RC_TRY(exchange(s));
+        for (Shard &sh : s->shards) {
+            if (multi) CU_TRY(cudaSetDevice(sh.device));
+            launch_winner(s, sh, with_trace);
+        }
+    }
+    for (Shard &sh : s->shards) {
+        if (multi) CU_TRY(cudaSetDevice(sh.device));
+        const bool timed = time_pivot && &sh == &s->shards[0];
+        if (timed) {
+            if (sh.ev_pivot.size() < s->ev_used + 2) {
+                cudaEvent_t a, b;
+                CU_TRY(cudaEventCreate(&a));
+                CU_TRY(cudaEventCreate(&b));
+                sh.ev_pivot.push_back(a);
+                sh.ev_pivot.push_back(b);
+            }
+            CU_TRY(cudaEventRecord(sh.ev_pivot[s->ev_used], sh.stream));
+        }
+        launch_pivot(s, sh);
+        if (timed) {
+            CU_TRY(cudaEventRecord(sh.ev_pivot[s->ev_used + 1], sh.stream));
+            s->ev_used += 2;
+        }
+    }
+    CU_TRY(cudaGetLastError());
+    return B200LP_OK;
+}
+
+static int default_poll_interval(const b200lp_solver *s)
+{
+    if (s->opts.poll_interval > 0) return s->opts.poll_interval;
+    return 32;
+}
+
+// n-solve-tableau's loop, src/simplex.lisp:455-460, for at most `limit` more pivots.
+static int iterate_locked(b200lp_solver *s, int64_t limit, b200lp_result *out, int32_t *trace_j,
+                          int32_t *trace_r)
+{
+    const double t0 = now_ms();
+    if (limit <= 0) limit = s->opts.max_iters;
+    const long long start_iters = s->iters_done;
+    const long long cap = limit > 0 ? start_iters + limit : 0;
+    const int64_t launches0 = s->kernel_launches;
+    s->ev_used = 0;
+    RC_TRY(push_state(s, ST_RUNNING, cap, -1, -1));
+    const bool time_pivot = s->opts.time_kernels != 0;
+    const int batch = default_poll_interval(s);
+    Shard &s0 = s->shards[0];
+    CU_TRY(cudaSetDevice(s0.device));
+    CU_TRY(cudaEventRecord(s0.ev_begin, s0.stream));
+
+    DevState last;
+    std::memset(&last, 0, sizeof(last));
+    last.status = ST_RUNNING;
+    int slot = 0;
+    bool pending[2] = {false, false};
+    long long enqueued = 0;
+    for (;;) {
+        // do not run more than two polls ahead, and never past the cap by more than a batch
+        for (int b = 0; b < batch; ++b) {
+            RC_TRY(enqueue_iteration(s, true, true, time_pivot && s->ev_used < 2 * 8192));
+            ++enqueued;
+        }
+        if (s->shards.size() > 1) CU_TRY(cudaSetDevice(s0.device));
+        CU_TRY(cudaMemcpyAsync(&s0.h_st[slot], s0.st, sizeof(DevState), cudaMemcpyDeviceToHost,
+                               s0.stream));
+        CU_TRY(cudaEventRecord(s0.ev_poll[slot], s0.stream));
+        pending[slot] = true;
+        const int other = slot ^ 1;
+        if (pending[other]) {
+            CU_TRY(cudaEventSynchronize(s0.ev_poll[other]));
+            pending[other] = false;
+            last = s0.h_st[other];
+            if (last.status != ST_RUNNING) break;
+        }
+        slot = other;
+    }
+    // drain: the newest poll holds the final state
+    for (int k = 0; k < 2; ++k) {
+        if (pending[k]) {
+            CU_TRY(cudaEventSynchronize(s0.ev_poll[k]));
+            if (s0.h_st[k].iters >= last.iters) last = s0.h_st[k];
+        }
+    }
+    CU_TRY(cudaEventRecord(s0.ev_end, s0.stream));
+    for (Shard &sh : s->shards) {
+        CU_TRY(cudaSetDevice(sh.device));
+        CU_TRY(cudaStreamSynchronize(sh.stream));
+    }
+    CU_TRY(cudaSetDevice(s0.device));
+    s->iters_done = last.iters;
+    const int status = last.status;
+
+    if (out) {
+        std::memset(out, 0, sizeof(*out));
+        out->status = status;
+        out->n_devices = s->world;
+        out->iterations = s->iters_done - start_iters;
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, s0.ev_begin, s0.ev_end));
+        out->ms_solve = ms;
+        double pk = 0.0;
+        // only launches that did real work: the first `iterations` timed pairs
+        const size_t real = (size_t)std::min<long long>(out->iterations, (long long)(s->ev_used / 2));
+        for (size_t k = 0; k < real; ++k) {
+            float e = 0.f;
+            CU_TRY(cudaEventElapsedTime(&e, s0.ev_pivot[2 * k], s0.ev_pivot[2 * k + 1]));
+            pk += e;
+        }
+        out->ms_pivot_kernel = pk;
+        out->pivot_kernel_launches = (int64_t)real;
+        out->kernel_launches = s->kernel_launches - launches0;
+        out->bytes_per_pivot = 16 * (int64_t)s0.R_local * s->C;
+        double obj = 0.0;
+        CU_TRY(cudaMemcpy(&obj, s0.tab + (int64_t)s0.m_local * s0.ld + (s->C - 1), sizeof(double),
+                          cudaMemcpyDeviceToHost));
+        out->objective = obj;
+        out->d2h_bytes += sizeof(double);
+        int tl = 0;
+        if (s->opts.trace_capacity > 0 && s0.trace) {
+            tl = (int)std::min<long long>(s->iters_done, s->opts.trace_capacity);
+            if (tl > 0 && (trace_j || trace_r)) {
+                CU_TRY(cudaMemcpy(s0.h_trace, s0.trace, sizeof(int2) * tl, cudaMemcpyDeviceToHost));
+                for (int k = 0; k < tl; ++k) {
+                    if (trace_j) trace_j[k] = s0.h_trace[k].x;
+                    if (trace_r) trace_r[k] = s0.h_trace[k].y;
+                }
+                out->d2h_bytes += sizeof(int2) * tl;
+            }
+        }
+        out->trace_len = tl;
+        out->ms_total = now_ms() - t0;
+    }
+    (void)enqueued;
+    return status;
+}
+
+static int upload_locked(b200lp_solver *s, const double *tab, int64_t ld, const int32_t *basis)
+{
+    if (!tab || ld < s->C) return fail(B200LP_ERR_INVALID_ARG, "upload", "ld < C or null tableau");
+    const size_t wbytes = sizeof(double) * s->C;
+    for (Shard &sh : s->shards) {
+        CU_TRY(cudaSetDevice(sh.device));
+        if (s->multiprocess || s->shards.size() == 1) {
+            // local block: R_local rows, objective last
+            CU_TRY(cudaMemcpy2DAsync(sh.tab, sizeof(double) * sh.ld, tab, sizeof(double) * ld,
+                                     wbytes, sh.R_local, cudaMemcpyHostToDevice, sh.stream));
+            if (basis && sh.m_local > 0)
+                CU_TRY(cudaMemcpyAsync(sh.basis, basis, sizeof(int32_t) * sh.m_local,
+                                       cudaMemcpyHostToDevice, sh.stream));
+        } else {
+            // in-process sharding: scatter row blocks of the full tableau, replicate the objective
+            if (sh.m_local > 0)
+                CU_TRY(cudaMemcpy2DAsync(sh.tab, sizeof(double) * sh.ld, tab + sh.row0 * ld,
+                                         sizeof(double) * ld, wbytes, sh.m_local,
+                                         cudaMemcpyHostToDevice, sh.stream));
+            CU_TRY(cudaMemcpyAsync(sh.tab + (int64_t)sh.m_local * sh.ld, tab + s->m * ld, wbytes,
+                                   cudaMemcpyHostToDevice, sh.stream));
+            if (basis && sh.m_local > 0)
+                CU_TRY(cudaMemcpyAsync(sh.basis, basis + sh.row0, sizeof(int32_t) * sh.m_local,
+                                       cudaMemcpyHostToDevice, sh.stream));
+        }
+        if (sh.ld > s->C)
+            k_zero_pad<<<64, 256, 0, sh.stream>>>(sh.tab, sh.ld, sh.R_local, (int)s->C);
+    }
+    for (Shard &sh : s->shards) {
+        CU_TRY(cudaSetDevice(sh.device));
+        CU_TRY(cudaStreamSynchronize(sh.stream));
+    }
+    CU_TRY(cudaGetLastError());
+    s->iters_done = 0;
+    return B200LP_OK;
+}
+
+static int download_locked(b200lp_solver *s, double *tab, int64_t ld, int32_t *basis)
+{
+    if (tab && ld < s->C) return fail(B200LP_ERR_INVALID_ARG, "download", "ld < C");
+    const size_t wbytes = sizeof(double) * s->C;
+    for (Shard &sh : s->shards) {
+        CU_TRY(cudaSetDevice(sh.device));
+        const bool local = s->multiprocess || s->shards.size() == 1;
+        if (tab) {
+            if (local) {
+                CU_TRY(cudaMemcpy2DAsync(tab, sizeof(double) * ld, sh.tab, sizeof(double) * sh.ld,
+                                         wbytes, sh.R_local, cudaMemcpyDeviceToHost, sh.stream));
+            } else {
+                if (sh.m_local > 0)
+                    CU_TRY(cudaMemcpy2DAsync(tab + sh.row0 * ld, sizeof(double) * ld, sh.tab,
+                                             sizeof(double) * sh.ld, wbytes, sh.m_local,
+                                             cudaMemcpyDeviceToHost, sh.stream));
+                if (&sh == &s->shards[0])
+                    CU_TRY(cudaMemcpyAsync(tab + s->m * ld, sh.tab + (int64_t)sh.m_local * sh.ld,
+                                           wbytes, cudaMemcpyDeviceToHost, sh.stream));
+            }
+        }
+        if (basis && sh.m_local > 0)
+            CU_TRY(cudaMemcpyAsync(basis + (local ? 0 : sh.row0), sh.basis,
+                                   sizeof(int32_t) * sh.m_local, cudaMemcpyDeviceToHost, sh.stream));
+    }
+    for (Shard &sh : s->shards) {
+        CU_TRY(cudaSetDevice(sh.device));
+        CU_TRY(cudaStreamSynchronize(sh.stream));
+    }
+    return B200LP_OK;
+}
+
+static int download_solution_locked(b200lp_solver *s, double *rhs, double *obj_row, int32_t *basis)
+{
+    const bool local = s->multiprocess || s->shards.size() == 1;
+    for (Shard &sh : s->shards) {
+        CU_TRY(cudaSetDevice(sh.device));
+        if (rhs) {
+            k_gather_col<<<(sh.R_local + 255) / 256, 256, 0, sh.stream>>>(sh.tab, sh.ld, sh.R_local,
+                                                                          (int)(s->C - 1), sh.colout);
+            s->kernel_launches++;
+            if (local) {
+                CU_TRY(cudaMemcpyAsync(rhs, sh.colout, sizeof(double) * sh.R_local,
+                                       cudaMemcpyDeviceToHost, sh.stream));
+            } else {
+                if (sh.m_local > 0)
+                    CU_TRY(cudaMemcpyAsync(rhs + sh.row0, sh.colout, sizeof(double) * sh.m_local,
+                                           cudaMemcpyDeviceToHost, sh.stream));
+                if (&sh == &s->shards[0])
+                    CU_TRY(cudaMemcpyAsync(rhs + s->m, sh.colout + sh.m_local, sizeof(double),
+                                           cudaMemcpyDeviceToHost, sh.stream));
+            }
+        }
+        if (obj_row && &sh == &s->shards[0])
+            CU_TRY(cudaMemcpyAsync(obj_row, sh.tab + (int64_t)sh.m_local * sh.ld,
+                                   sizeof(double) * s->C, cudaMemcpyDeviceToHost, sh.stream));
+        if (basis && sh.m_local > 0)
+            CU_TRY(cudaMemcpyAsync(basis + (local ? 0 : sh.row0), sh.basis,
+                                   sizeof(int32_t) * sh.m_local, cudaMemcpyDeviceToHost, sh.stream));
+    }
+    for (Shard &sh : s->shards) {
+        CU_TRY(cudaSetDevice(sh.device));
+        CU_TRY(cudaStreamSynchronize(sh.stream));
+    }
+    CU_TRY(cudaGetLastError());
+    return B200LP_OK;
+}
+
+static int create_common(const b200lp_opts *opts, int64_t R, int64_t C, int32_t is_max,
+                         b200lp_solver **out)
+{
+    if (!out) return fail(B200LP_ERR_INVALID_ARG, "create", "null out pointer");
+    *out = nullptr;
+    if (R < 2 || C < 2 || R > (1ll << 30) || C > (1ll << 30))
+        return fail(B200LP_ERR_INVALID_ARG, "create", "need R >= 2, C >= 2");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        (void)cudaGetLastError();
+        return fail(B200LP_ERR_NO_DEVICE, "cudaGetDeviceCount",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "no CUDA device");
+    }
+    b200lp_solver *s = new (std::nothrow) b200lp_solver();
+    if (!s) return fail(B200LP_ERR_OUT_OF_MEMORY, "create", "host allocation");
+    if (opts) s->opts = *opts; else std::memset(&s->opts, 0, sizeof(s->opts));
+    s->R = R; s->C = C; s->m = R - 1; s->is_max = is_max ? 1 : 0;
+    fill_thresholds(s);
+    *out = s;
+    return B200LP_OK;
+}
+
+static int ensure_nccl()
+{
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    const char *why = "";
+    if (!g_nccl.load(&why)) return fail(B200LP_ERR_NCCL, "NCCL", why);
+    return B200LP_OK;
+}
+
+} // namespace b200lp
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+void b200lp_thresholds(double tol, double *enter, double *pivot, double *feas)
+{
+    if (!(tol > 0)) tol = 1024.0;
+    if (enter) *enter = (tol / 8.0) * kClEps;   // src/simplex.lisp:370-371, 377-378
+    if (pivot) *pivot = (tol / 2.0) * kClEps;   // src/simplex.lisp:386-387
+    if (feas) *feas = tol * kClEps;             // src/simplex.lisp:405-406
+}
+
+void b200lp_partition(int64_t m, int32_t nranks, int32_t rank, int64_t *row_begin, int64_t *row_end)
+{
+    if (nranks < 1) nranks = 1;
+    const int64_t per = (m + nranks - 1) / nranks;
+    int64_t b = std::min<int64_t>(m, per * rank);
+    int64_t e = std::min<int64_t>(m, b + per);
+    if (row_begin) *row_begin = b;
+    if (row_end) *row_end = e;
+}
+
+int b200lp_version(void) { return B200LP_VERSION; }
+
+int b200lp_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *b200lp_last_error(void) { return g_last_error.c_str(); }
+
+const char *b200lp_strerror(int code)
+{
+    switch (code) {
+    case B200LP_OK: return "optimal";
+    case B200LP_UNBOUNDED: return "Problem is unbounded";
+    case B200LP_INFEASIBLE: return "Problem has no feasible region";
+    case B200LP_ITERATION_LIMIT: return "iteration limit reached";
+    case B200LP_ARTIFICIAL_STUCK: return "Artificial variable still in basis and cannot be replaced";
+    case B200LP_ERR_INVALID_ARG: return "invalid argument";
+    case B200LP_ERR_CUDA: return "CUDA error";
+    case B200LP_ERR_NCCL: return "NCCL error";
+    case B200LP_ERR_NO_DEVICE: return "no CUDA device";
+    case B200LP_ERR_OUT_OF_MEMORY: return "out of device memory";
+    case B200LP_ERR_INTERNAL: return "internal error";
+    default: return "unknown status";
+    }
+}
+
+int b200lp_create(const b200lp_opts *opts, int64_t R, int64_t C, int32_t is_max,
+                  b200lp_solver **out)
+{
+    try {
+        RC_TRY(create_common(opts, R, C, is_max, out));
+        b200lp_solver *s = *out;
+        const int nd = std::max(1, (int)s->opts.ndev);
+        if (nd > B200LP_MAX_DEVICES || nd > s->m) {
+            b200lp_destroy(s); *out = nullptr;
+            return fail(B200LP_ERR_INVALID_ARG, "create", "ndev out of range");
+        }
+        s->world = nd;
+        s->multiprocess = false;
+        s->shards.resize(nd);
+        for (int g = 0; g < nd; ++g) {
+            Shard &sh = s->shards[g];
+            sh.device = s->opts.devices[g];
+            if (s->opts.ndev == 0) sh.device = s->opts.devices[0];
+            sh.rank = g;
+            int64_t b, e;
+            b200lp_partition(s->m, nd, g, &b, &e);
+            sh.row0 = b; sh.m_local = (int)(e - b); sh.R_local = sh.m_local + 1;
+        }
+        int rc = B200LP_OK;
+        for (Shard &sh : s->shards) { rc = alloc_shard(s, sh); if (rc) break; }
+        if (!rc && nd > 1) {
+            rc = ensure_nccl();
+            if (!rc) {
+                std::vector<ncclComm_t> comms(nd);
+                std::vector<int> devs(nd);
+                for (int g = 0; g < nd; ++g) devs[g] = s->shards[g].device;
+                ncclResult_t r = g_nccl.CommInitAll(comms.data(), nd, devs.data());
+                if (r != ncclSuccess) rc = fail(B200LP_ERR_NCCL, "ncclCommInitAll", g_nccl.GetErrorString(r));
+                else for (int g = 0; g < nd; ++g) s->shards[g].comm = comms[g];
+            }
+        }
+        if (rc) { b200lp_destroy(s); *out = nullptr; return rc; }
+        return B200LP_OK;
+    } catch (const std::exception &ex) {
+        return fail(B200LP_ERR_INTERNAL, "create", ex.what());
+    }
+}
+
+int b200lp_comm_unique_id(void *unique_id_128)
+{
+    if (!unique_id_128) return fail(B200LP_ERR_INVALID_ARG, "comm_unique_id", "null");
+    RC_TRY(ensure_nccl());
+    ncclUniqueId id;
+    NCCL_TRY(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(unique_id_128, &id, 128);
+    return B200LP_OK;
+}
+
+int b200lp_create_sharded(const b200lp_opts *opts, int64_t R, int64_t C, int32_t is_max,
+                          int32_t rank, int32_t nranks, const void *unique_id_128,
+                          b200lp_solver **out)
+{
+    try {
+        if (nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !unique_id_128))
+            return fail(B200LP_ERR_INVALID_ARG, "create_sharded", "bad rank/nranks/id");
+        RC_TRY(create_common(opts, R, C, is_max, out));
+        b200lp_solver *s = *out;
+        if (nranks > s->m) {
+            b200lp_destroy(s); *out = nullptr;
+            return fail(B200LP_ERR_INVALID_ARG, "create_sharded", "more ranks than rows");
+        }
+        s->world = nranks;
+        s->multiprocess = true;
+        s->shards.resize(1);
+        Shard &sh = s->shards[0];
+        sh.device = s->opts.devices[0];
+        sh.rank = rank;
+        int64_t b, e;
+        b200lp_partition(s->m, nranks, rank, &b, &e);
+        sh.row0 = b; sh.m_local = (int)(e - b); sh.R_local = sh.m_local + 1;
+        int rc = alloc_shard(s, sh);
+        if (!rc && nranks > 1) {
+            rc = ensure_nccl();
+            if (!rc) {
+                ncclUniqueId id;
+                std::memcpy(&id, unique_id_128, 128);
+                ncclResult_t r = g_nccl.CommInitRank(&sh.comm, nranks, id, rank);
+                if (r != ncclSuccess) rc = fail(B200LP_ERR_NCCL, "ncclCommInitRank", g_nccl.GetErrorString(r));
+            }
+        }
+        if (rc) { b200lp_destroy(s); *out = nullptr; return rc; }
+        return B200LP_OK;
+    } catch (const std::exception &ex) {
+        return fail(B200LP_ERR_INTERNAL, "create_sharded", ex.what());
+    }
+}
+
+int b200lp_shard_rows(const b200lp_solver *s, int64_t *row_begin, int64_t *row_end)
+{
+    if (!s || s->shards.empty()) return fail(B200LP_ERR_INVALID_ARG, "shard_rows", "null solver");
+    if (row_begin) *row_begin = s->shards.front().row0;
+    if (row_end) *row_end = s->shards.back().row0 + s->shards.back().m_local;
+    return B200LP_OK;
+}
+
+void b200lp_destroy(b200lp_solver *s)
+{
+    if (!s) return;
+    for (Shard &sh : s->shards) free_shard(sh);
+    delete s;
+}
+
+int b200lp_upload(b200lp_solver *s, const double *tab, int64_t ld, const int32_t *basis)
+{
+    if (!s) return fail(B200LP_ERR_INVALID_ARG, "upload", "null solver");
+    std::lock_guard<std::mutex> lk(s->mu);
+    return upload_locked(s, tab, ld, basis);
+}
+
+int b200lp_download(b200lp_solver *s, double *tab, int64_t ld, int32_t *basis)
+{
+    if (!s) return fail(B200LP_ERR_INVALID_ARG, "download", "null solver");
+    std::lock_guard<std::mutex> lk(s->mu);
+    return download_locked(s, tab, ld, basis);
+}
+
+int b200lp_download_solution(b200lp_solver *s, double *rhs, double *obj_row, int32_t *basis)
+{
+    if (!s) return fail(B200LP_ERR_INVALID_ARG, "download_solution", "null solver");
+    std::lock_guard<std::mutex> lk(s->mu);
+    return download_solution_locked(s, rhs, obj_row, basis);
+}
+
+int b200lp_find_entering_column(b200lp_solver *s, int64_t *col)
+{
+    if (!s || !col) return fail(B200LP_ERR_INVALID_ARG, "find_entering_column", "null");
+    std::lock_guard<std::mutex> lk(s->mu);
+    RC_TRY(push_state(s, ST_RUNNING, 0, -1, -1));
+    for (Shard &sh : s->shards) { CU_TRY(cudaSetDevice(sh.device)); launch_enter(s, sh); }
+    DevState st;
+    RC_TRY(pull_state(s, &st));
+    *col = (st.status == ST_RUNNING) ? st.j : -1;
+    return B200LP_OK;
+}
+
+int b200lp_find_pivoting_row(b200lp_solver *s, int64_t j, int64_t *row)
+{
+    if (!s || !row) return fail(B200LP_ERR_INVALID_ARG, "find_pivoting_row", "null");
+    if (j < 0 || j >= s->C) return fail(B200LP_ERR_INVALID_ARG, "find_pivoting_row", "column out of range");
+    std::lock_guard<std::mutex> lk(s->mu);
+    RC_TRY(push_state(s, ST_RUNNING, 0, (int)j, -1));
+    for (Shard &sh : s->shards) { CU_TRY(cudaSetDevice(sh.device)); launch_ratio(s, sh, false); }
+    if (s->world > 1) {
+        // candidates travel with their header only being meaningful; rows may be stale
+        RC_TRY(exchange(s));
+        for (Shard &sh : s->shards) { CU_TRY(cudaSetDevice(sh.device)); launch_winner(s, sh, false); }
+    }
+    DevState st;
+    RC_TRY(pull_state(s, &st));
+    *row = (st.status == ST_RUNNING) ? st.p : -1;
+    return B200LP_OK;
+}
+
+int b200lp_pivot(b200lp_solver *s, int64_t j, int64_t r)
+{
+    if (!s) return fail(B200LP_ERR_INVALID_ARG, "pivot", "null solver");
+    if (j < 0 || j >= s->C || r < 0 || r >= s->m)
+        return fail(B200LP_ERR_INVALID_ARG, "pivot", "row/column out of range");
+    std::lock_guard<std::mutex> lk(s->mu);
+    RC_TRY(push_state(s, ST_RUNNING, 0, (int)j, (int)r));
+    RC_TRY(enqueue_iteration(s, false, false, false));
+    DevState st;
+    RC_TRY(pull_state(s, &st));
+    s->iters_done = st.iters;
+    return B200LP_OK;
+}
+
+int b200lp_iterate(b200lp_solver *s, int64_t max_iters, b200lp_result *out, int32_t *trace_j,
+                   int32_t *trace_r)
+{
+    if (!s) return fail(B200LP_ERR_INVALID_ARG, "iterate", "null solver");
+    std::lock_guard<std::mutex> lk(s->mu);
+    try {
+        return iterate_locked(s, max_iters, out, trace_j, trace_r);
+    } catch (const std::exception &ex) {
+        return fail(B200LP_ERR_INTERNAL, "iterate", ex.what());
+    }
+}
+
+int b200lp_solve(const b200lp_opts *opts, double *tab, int64_t R, int64_t C, int64_t ld,
+                 int32_t *basis, int32_t is_max, b200lp_result *out, int32_t *trace_j,
+                 int32_t *trace_r)
+{
+    if (!tab || !basis || ld < C) return fail(B200LP_ERR_INVALID_ARG, "solve", "null buffer or ld < C");
+    const double t0 = now_ms();
+    b200lp_solver *s = nullptr;
+    RC_TRY(b200lp_create(opts, R, C, is_max, &s));
+    b200lp_result res;
+    std::memset(&res, 0, sizeof(res));
+    int rc = B200LP_OK;
+    double t_h2d = now_ms();
+    rc = b200lp_upload(s, tab, ld, basis);
+    const double ms_h2d = now_ms() - t_h2d;
+    int status = rc;
+    if (rc == B200LP_OK) {
+        status = b200lp_iterate(s, 0, &res, trace_j, trace_r);
+        if (status >= 0) {
+            const double t_d2h = now_ms();
+            if (s->opts.writeback_full) {
+                rc = b200lp_download(s, tab, ld, basis);
+                res.d2h_bytes += (int64_t)sizeof(double) * R * C + (int64_t)sizeof(int32_t) * (R - 1);
+            } else {
+                // only what the accessors read (src/simplex.lisp:74-120): RHS column, objective
+                // row, basis.  Staged through contiguous host buffers, then scattered into `tab`.
+                std::vector<double> rhs((size_t)R), obj((size_t)C);
+                rc = b200lp_download_solution(s, rhs.data(), obj.data(), basis);
+                if (rc == B200LP_OK) {
+                    for (int64_t i = 0; i < R; ++i) tab[i * ld + (C - 1)] = rhs[(size_t)i];
+                    std::memcpy(tab + (R - 1) * ld, obj.data(), sizeof(double) * C);
+                }
+                res.d2h_bytes += (int64_t)sizeof(double) * (R + C) + (int64_t)sizeof(int32_t) * (R - 1);
+            }
+            res.ms_d2h = now_ms() - t_d2h;
+            if (rc != B200LP_OK) status = rc;
+        }
+    }
+    b200lp_destroy(s);
+    res.status = status;
+    res.ms_h2d = ms_h2d;
+    res.h2d_bytes = (int64_t)sizeof(double) * R * C + (int64_t)sizeof(int32_t) * (R - 1);
+    res.ms_total = now_ms() - t0;
+    if (out) *out = res;
+    return status;
+}
+
+// Two-phase driver: src/simplex.lisp:402-452.  Single device (the transition's objective
+// re-pricing is order dependent across all rows; BASELINE's sharded configs never need it).
+int b200lp_solve_two_phase(const b200lp_opts *opts, double *art_tab, int64_t C_art, int64_t ld_art,
+                           int32_t *art_basis, double *main_tab, int64_t R, int64_t C, int64_t ld,
+                           int32_t *main_basis, int32_t is_max, b200lp_result *out)
+{
+    if (!art_tab || !art_basis || !main_tab || !main_basis || ld_art < C_art || ld < C || C_art < C)
+        return fail(B200LP_ERR_INVALID_ARG, "solve_two_phase", "null buffer or bad dimensions");
+    if (opts && opts->ndev > 1)
+        return fail(B200LP_ERR_INVALID_ARG, "solve_two_phase", "two-phase runs on one device");
+    const double t0 = now_ms();
+    b200lp_solver *art = nullptr, *mn = nullptr;
+    b200lp_result r1, r2;
+    std::memset(&r1, 0, sizeof(r1));
+    std::memset(&r2, 0, sizeof(r2));
+    int64_t cleanup = 0;
+    int status = B200LP_OK;
+    unsigned char *d_is_basic = nullptr;
+    int *d_newcol = nullptr;
+    double *d_scales = nullptr;
+    auto finish = [&](int st) {
+        if (art) { cudaSetDevice(art->shards[0].device); }
+        cudaFree(d_is_basic); cudaFree(d_newcol); cudaFree(d_scales);
+        b200lp_destroy(art); b200lp_destroy(mn);
+        if (out) {
+            *out = r2;
+            out->status = st;
+            out->iterations_phase1 = r1.iterations;
+            out->iterations_cleanup = cleanup;
+            out->ms_solve = r1.ms_solve + r2.ms_solve;
+            out->kernel_launches = r1.kernel_launches + r2.kernel_launches;
+            out->h2d_bytes = (int64_t)sizeof(double) * R * (C + C_art);
+            out->ms_total = now_ms() - t0;
+        }
+        return st;
+    };
+    const int64_t m = R - 1, nv = C - 1, art_nv = C_art - 1;
+    int rc = b200lp_create(opts, R, C_art, /*is_max=*/0, &art);   // phase 1 is a `min` problem
+    if (rc) return finish(rc);
+    rc = b200lp_create(opts, R, C, is_max, &mn);
+    if (rc) return finish(rc);
+    if ((rc = b200lp_upload(art, art_tab, ld_art, art_basis))) return finish(rc);
+    if ((rc = b200lp_upload(mn, main_tab, ld, main_basis))) return finish(rc);
+
+    status = b200lp_iterate(art, 0, &r1, nullptr, nullptr);
+    if (status != B200LP_OK) return finish(status);
+    // (unless (fp= 0 obj tol) (error 'infeasible-problem-error))  :405-407
+    if (!(std::fabs(0.0 - r1.objective) <= art->thr_feas)) return finish(B200LP_INFEASIBLE);
+
+    Shard &as = art->shards[0];
+    Shard &ms = mn->shards[0];
+    std::vector<int32_t> hb((size_t)m);
+#define TP_CU(expr)                                                                     \
+    do {                                                                                \
+        cudaError_t e__ = (expr);                                                       \
+        if (e__ != cudaSuccess) {                                                       \
+            fail(B200LP_ERR_CUDA, #expr, cudaGetErrorString(e__));                      \
+            return finish(B200LP_ERR_CUDA);                                             \
+        }                                                                               \
+    } while (0)
+    TP_CU(cudaSetDevice(as.device));
+    TP_CU(cudaMemcpy(hb.data(), as.basis, sizeof(int32_t) * m, cudaMemcpyDeviceToHost));
+    // drive zero-level artificial variables out of the basis  :419-434
+    bool any_art = false;
+    for (int64_t i = 0; i < m; ++i) any_art |= hb[(size_t)i] >= nv;
+    if (any_art) {
+        TP_CU(cudaMalloc(&d_is_basic, (size_t)C_art));
+        TP_CU(cudaMalloc(&d_newcol, sizeof(int)));
+        std::vector<unsigned char> is_basic((size_t)C_art);
+        for (int64_t i = 0; i < m; ++i) {
+            if (hb[(size_t)i] < nv) continue;
+            double rhs = 0.0;
+            TP_CU(cudaMemcpy(&rhs, as.tab + i * as.ld + art_nv, sizeof(double), cudaMemcpyDeviceToHost));
+            if (rhs != 0.0) return finish(B200LP_ARTIFICIAL_STUCK);
+            std::fill(is_basic.begin(), is_basic.end(), 0);
+            for (int64_t k = 0; k < m; ++k) is_basic[(size_t)hb[(size_t)k]] = 1;
+            TP_CU(cudaMemcpy(d_is_basic, is_basic.data(), (size_t)C_art, cudaMemcpyHostToDevice));
+            k_first_nonzero_nonbasic<<<1, 1024, 0, as.stream>>>(as.tab + i * as.ld, (int)nv,
+                                                                d_is_basic, d_newcol);
+            int new_col = -1;
+            TP_CU(cudaMemcpyAsync(&new_col, d_newcol, sizeof(int), cudaMemcpyDeviceToHost, as.stream));
+            TP_CU(cudaStreamSynchronize(as.stream));
+            if (new_col < 0) return finish(B200LP_ARTIFICIAL_STUCK);
+            if ((rc = b200lp_pivot(art, new_col, i))) return finish(rc);
+            hb[(size_t)i] = new_col;
+            ++cleanup;
+        }
+    }
+    // copy coefficients/RHS (:437-441), basis and objective re-pricing (:444-451)
+    {
+        dim3 grid((unsigned)std::min<int64_t>((nv + 256) / 256, 64), (unsigned)std::min<int64_t>(m, 32768));
+        k_copy_art_to_main<<<grid, 256, 0, ms.stream>>>(as.tab, as.ld, (int)art_nv, ms.tab, ms.ld,
+                                                        (int)nv, (int)m);
+        TP_CU(cudaMemcpyAsync(ms.basis, as.basis, sizeof(int32_t) * m, cudaMemcpyDeviceToDevice, ms.stream));
+        TP_CU(cudaMalloc(&d_scales, sizeof(double) * m));
+        k_reprice_scales<<<(unsigned)((m + 255) / 256), 256, 0, ms.stream>>>(
+            ms.tab + m * ms.ld, ms.basis, (int)m, d_scales);
+        k_reprice<<<(unsigned)((nv + 1 + 127) / 128), 128, 0, ms.stream>>>(ms.tab, ms.ld, (int)m,
+                                                                          (int)nv, d_scales);
+        TP_CU(cudaStreamSynchronize(ms.stream));
+        TP_CU(cudaGetLastError());
+    }
+    status = b200lp_iterate(mn, 0, &r2, nullptr, nullptr);
+    if (status >= 0) {
+        if (opts && opts->writeback_full) {
+            if ((rc = b200lp_download(art, art_tab, ld_art, art_basis))) return finish(rc);
+            if ((rc = b200lp_download(mn, main_tab, ld, main_basis))) return finish(rc);
+        } else {
+            std::vector<double> rhs((size_t)R), obj((size_t)C);
+            if ((rc = b200lp_download_solution(mn, rhs.data(), obj.data(), main_basis))) return finish(rc);
+            for (int64_t i = 0; i < R; ++i) main_tab[i * ld + (C - 1)] = rhs[(size_t)i];
+            std::memcpy(main_tab + (R - 1) * ld, obj.data(), sizeof(double) * C);
+        }
+    }
+#undef TP_CU
+    return finish(status);
+}
+
+} // extern "C"

@@ -1,0 +1,53 @@
+"""Synthetic dense LPs of BASELINE.json's configs: max c.x s.t. Ax <= b, x >= 0.
+
+numpy default_rng(seed) (PCG64), draws in the order A (row-major m x n), b, c; all fp64.
+The tableau is what the reference's build-tableau produces for such a problem
+(src/simplex.lisp:214-287): rows 0..m-1 = [A | I_m | b], row m = [-c | 0 | 0], basis[i] = n+i.
+"""
+import numpy as np
+
+
+def dense_lp(m, n, seed=1234, degenerate=False):
+    """A ~ U[0,1), b ~ U[n/8, 3n/8), c ~ U[0,1).
+
+    degenerate=True is config 5: small-integer data with exact ratio ties.  The first half of
+    the rows are cone constraints through the origin (A in {-1,0,1}, b = 0: every ratio there
+    is exactly 0, so the leaving row is decided by the tie-break alone); the second half
+    (A in {0,1,2}, b in {n/4, n/2, 3n/4}) bounds the polytope; c in {1,2,3}."""
+    rng = np.random.default_rng(seed)
+    if degenerate:
+        A = rng.integers(0, 3, size=(m, n)).astype(np.float64)
+        b = rng.integers(1, 4, size=m).astype(np.float64) * n / 4.0
+        c = rng.integers(1, 4, size=n).astype(np.float64)
+        half = m // 2
+        A[:half] = rng.integers(-1, 2, size=(half, n))
+        b[:half] = 0.0
+        return A, b, c
+    A = rng.random((m, n))
+    b = rng.uniform(n / 8.0, 3.0 * n / 8.0, m)
+    c = rng.random(n)
+    return A, b, c
+
+
+def tableau_from_lp(A, b, c, out=None):
+    """[A | I | b ; -c | 0 | 0] as a row-major (m+1) x (n+m+1) fp64 matrix plus the slack basis."""
+    m, n = A.shape
+    R, C = m + 1, n + m + 1
+    tab = out if out is not None else np.zeros((R, C))
+    if out is not None:
+        tab[:] = 0.0
+    tab[:m, :n] = A
+    tab[np.arange(m), n + np.arange(m)] = 1.0
+    tab[:m, C - 1] = b
+    tab[m, :n] = -c
+    basis = np.arange(n, n + m, dtype=np.int32)
+    return tab, basis
+
+
+def dense_tableau(m, n, seed=1234, degenerate=False, out=None):
+    A, b, c = dense_lp(m, n, seed, degenerate)
+    return tableau_from_lp(A, b, c, out=out)
+
+
+README_LP = dict(A=np.array([[2.0, 1.0, 0.0], [0.0, 1.0, 1.0]]), b=np.array([8.0, 7.0]),
+                 c=np.array([1.0, 4.0, 3.0]))  # README.md:30-62 -> obj 57/2, x=(1/2, 7, 0)

@@ -1,0 +1,309 @@
+"""Parity of the CUDA path (through the C ABI, ctypes) against the oracle -- bit-exact.
+
+Reads like the reference's t/simplex.lisp: pivot-row, basic-problem, equality-constraint,
+leq-constraint, unsolvable-problems, plus randomized differential tests the reference lacks.
+All tests need a real B200 (-m gpu).  The oracle is only the checker here.
+"""
+import numpy as np
+import pytest
+
+from golden import reference_goldens as G
+from linear_programming_b200 import _ffi, synthetic
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def f64(rows):
+    return np.array([[float(x) for x in r] for r in rows], dtype=np.float64)
+
+
+def i32(b):
+    return np.array(b, dtype=np.int32)
+
+
+def random_tableau(m, n, seed, signed=False):
+    rng = np.random.default_rng(seed)
+    A = rng.random((m, n)) - (0.25 if signed else 0.0)
+    b = rng.uniform(n / 8.0, 3.0 * n / 8.0, m)
+    c = rng.random(n)
+    return synthetic.tableau_from_lp(A, b, c)
+
+
+# ------------------------------------------------------------------ reference goldens
+def test_pivot_row_golden():
+    """t/simplex.lisp:135-159"""
+    g = G.SINGLE_PIVOT
+    tab, basis = f64(g["initial"]["matrix"]), i32(g["initial"]["basis"])
+    with _ffi.DeviceTableau(*tab.shape) as d:
+        d.upload(tab, basis)
+        d.pivot(g["col"], g["row"])
+        out, ob = d.download()
+    assert np.array_equal(out, f64(g["matrix"])) and ob.tolist() == g["basis"]
+    assert out[-1, -1] == 4.0
+
+
+def test_basic_problem_golden():
+    """t/simplex.lisp:170-194, README.md:58-62"""
+    g = G.BASIC_SOLVED
+    tab, basis = f64(g["initial"]["matrix"]), i32(g["initial"]["basis"])
+    st, res, trace = _ffi.solve(tab, basis, True, _ffi.make_opts(writeback_full=True, trace_capacity=8))
+    assert st == _ffi.OK and res.iterations == g["pivots"] and trace == g["trace"]
+    assert np.array_equal(tab, f64(g["matrix"])) and basis.tolist() == g["basis"]
+    assert res.objective == 28.5
+
+
+def test_basic_problem_partial_writeback_touches_only_solution_cells():
+    g = G.BASIC_SOLVED
+    tab, basis = f64(g["initial"]["matrix"]), i32(g["initial"]["basis"])
+    before = tab.copy()
+    st, res, _ = _ffi.solve(tab, basis, True)
+    want = f64(g["matrix"])
+    assert st == _ffi.OK
+    assert np.array_equal(tab[:, -1], want[:, -1]) and np.array_equal(tab[-1], want[-1])
+    assert np.array_equal(tab[:-1, :-1], before[:-1, :-1])      # interior left alone
+    assert basis.tolist() == g["basis"]
+
+
+@pytest.mark.parametrize("g", [G.EQ_SOLVED, G.GEQ_SOLVED], ids=["eq", "geq"])
+def test_two_phase_goldens(g):
+    """t/simplex.lisp:196-275"""
+    b = g["initial"]
+    art, ab = f64(b["art_matrix"]), i32(b["art_basis"])
+    main, mb = f64(b["main_matrix"]), i32(b["main_basis"])
+    o_art, o_ab, o_main, o_mb = art.copy(), ab.copy(), main.copy(), mb.copy()
+    st, res = _ffi.solve_two_phase(art, ab, main, mb, True, _ffi.make_opts(writeback_full=True))
+    ost, oits = oracle.solve_two_phase(o_art, o_ab, o_main, o_mb, True)
+    assert st == ost == _ffi.OK
+    assert (res.iterations_phase1, res.iterations_cleanup, res.iterations) == oits == g["pivots"]
+    assert ab.tolist() == g["art_basis"] and mb.tolist() == g["main_basis"]
+    assert np.array_equal(art, o_art) and np.array_equal(main, o_main)        # bit-exact vs oracle
+    np.testing.assert_allclose(main, f64(g["main_matrix"]), rtol=1e-14, atol=1e-14)
+    assert abs(res.objective - float(g["objective"])) <= 1e-8 * float(g["objective"])
+
+
+def test_unsolvable_problems():
+    """t/simplex.lisp:277-289"""
+    g = G.INFEASIBLE
+    st, _ = _ffi.solve_two_phase(f64(g["art_matrix"]), i32(g["art_basis"]),
+                                 f64(g["main_matrix"]), i32(g["main_basis"]), True)
+    assert st == _ffi.INFEASIBLE
+    g = G.UNBOUNDED
+    st, _, _ = _ffi.solve(f64(g["matrix"]), i32(g["basis"]), True)
+    assert st == _ffi.UNBOUNDED
+
+
+def test_assembly_problem():
+    """t/integration.lisp:32-58"""
+    g = G.ASSEMBLY
+    tab, basis = f64(g["matrix"]), i32(g["basis"])
+    o_tab, o_basis = tab.copy(), basis.copy()
+    st, res, _ = _ffi.solve(tab, basis, True, _ffi.make_opts(writeback_full=True))
+    oracle.solve(o_tab, o_basis, True)
+    assert st == _ffi.OK and res.iterations == g["pivots"]
+    assert np.array_equal(tab, o_tab) and np.array_equal(basis, o_basis)
+    lo, hi = g["bounds"]["revenue"]
+    assert lo <= res.objective <= hi
+
+
+# ------------------------------------------------------------- function-by-function parity
+@pytest.mark.parametrize("m,n,signed", [(37, 53, False), (200, 300, False), (129, 64, True)])
+def test_each_reference_function_matches_oracle(m, n, signed):
+    tab, basis = random_tableau(m, n, seed=m * 1000 + n, signed=signed)
+    o_tab, o_basis = tab.copy(), basis.copy()
+    with _ffi.DeviceTableau(*tab.shape) as d:
+        d.upload(tab, basis)
+        for it in range(25):
+            j = d.find_entering_column()
+            oj = oracle.find_entering_column(o_tab, True)
+            assert (j if j is not None else -1) == oj
+            if j is None:
+                break
+            r = d.find_pivoting_row(j)
+            orow = oracle.find_pivoting_row(o_tab, o_basis, j)
+            assert (r if r is not None else -1) == orow
+            if r is None:
+                break
+            d.pivot(j, r)
+            oracle.pivot(o_tab, o_basis, j, r)
+            g_tab, g_basis = d.download()
+            assert np.array_equal(g_tab, o_tab), f"tableau differs after pivot {it}"
+            assert np.array_equal(g_basis, o_basis)
+
+
+@pytest.mark.parametrize("m,n,is_max", [(64, 96, True), (256, 512, True), (100, 40, True),
+                                        (96, 160, False), (1, 3, True), (3, 1, True)])
+def test_full_solve_bit_exact(m, n, is_max):
+    tab, basis = random_tableau(m, n, seed=11 * m + n)
+    if not is_max:
+        tab[-1, :n] *= -1.0          # min (-c).x: the objective row (still -coef, :272) is +c
+    o_tab, o_basis = tab.copy(), basis.copy()
+    ost, oit, otrace = oracle.solve(o_tab, o_basis, is_max, trace_cap=100000)
+    st, res, trace = _ffi.solve(tab, basis, is_max,
+                                _ffi.make_opts(writeback_full=True, trace_capacity=100000))
+    assert st == ost and res.iterations == oit and trace == otrace
+    assert np.array_equal(tab, o_tab) and np.array_equal(basis, o_basis)
+    assert res.objective == o_tab[-1, -1]
+
+
+def test_config2_m1024_n2048_objective_and_basis():
+    """BASELINE config 2: objective within 1e-8 of the reference rule's answer (here: bit-exact)."""
+    tab, basis = synthetic.dense_tableau(1024, 2048, seed=1234)
+    o_tab, o_basis = tab.copy(), basis.copy()
+    ost, oit, otrace = oracle.solve(o_tab, o_basis, True, parallel=True, trace_cap=1 << 16)
+    st, res, trace = _ffi.solve(tab, basis, True, _ffi.make_opts(writeback_full=True,
+                                                                 trace_capacity=1 << 16))
+    assert st == ost == _ffi.OK and res.iterations == oit
+    assert trace == otrace
+    assert np.array_equal(basis, o_basis)
+    assert np.array_equal(tab, o_tab)
+    assert abs(res.objective - 545.8113461511593) <= 1e-8 * 545.8113461511593   # HiGHS, SURVEY 6
+
+
+def test_padded_host_leading_dimension():
+    tab0, basis = random_tableau(50, 70, seed=5)
+    wide = np.full((tab0.shape[0], tab0.shape[1] + 13), np.nan)
+    wide[:, :tab0.shape[1]] = tab0
+    view = wide[:, :tab0.shape[1]]
+    o_tab, o_basis = tab0.copy(), basis.copy()
+    oracle.solve(o_tab, o_basis, True)
+    st, res, _ = _ffi.solve(view, basis, True, _ffi.make_opts(writeback_full=True))
+    assert st == _ffi.OK and np.array_equal(view, o_tab) and np.array_equal(basis, o_basis)
+    assert np.isnan(wide[:, tab0.shape[1]:]).all()
+
+
+def test_iteration_limit_and_resume():
+    tab, basis = random_tableau(120, 200, seed=9)
+    o_tab, o_basis = tab.copy(), basis.copy()
+    ost, oit, otrace = oracle.solve(o_tab, o_basis, True, trace_cap=4096)
+    assert oit > 20
+    with _ffi.DeviceTableau(*tab.shape, opts=_ffi.make_opts(trace_capacity=4096)) as d:
+        d.upload(tab, basis)
+        st, res, _ = d.iterate(7)
+        assert st == _ffi.ITERATION_LIMIT and res.iterations == 7
+        st, res, _ = d.iterate(5)
+        assert st == _ffi.ITERATION_LIMIT and res.iterations == 5
+        st, res, trace = d.iterate(0)
+        assert st == _ffi.OK and res.iterations == oit - 12 and trace == otrace
+        g_tab, g_basis = d.download()
+    assert np.array_equal(g_tab, o_tab) and np.array_equal(g_basis, o_basis)
+    # one-shot call with opts.max_iters
+    st, res, _ = _ffi.solve(tab, basis, True, _ffi.make_opts(max_iters=3))
+    assert st == _ffi.ITERATION_LIMIT and res.iterations == 3
+
+
+def test_fp_tolerance_keyword_changes_thresholds_like_the_oracle():
+    tab, basis = random_tableau(60, 90, seed=21)
+    for tol in (1.0, 1024.0, 1e9):
+        o_tab, o_basis = tab.copy(), basis.copy()
+        ost, oit, otrace = oracle.solve(o_tab, o_basis, True, tol=tol, trace_cap=4096)
+        g_tab, g_basis = tab.copy(), basis.copy()
+        st, res, trace = _ffi.solve(g_tab, g_basis, True,
+                                    _ffi.make_opts(fp_tolerance=tol, writeback_full=True,
+                                                   trace_capacity=4096))
+        assert (st, res.iterations, trace) == (ost, oit, otrace)
+        assert np.array_equal(g_tab, o_tab)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9])
+def test_every_pivot_kernel_variant_is_bit_exact(variant):
+    tab, basis = random_tableau(150, 333, seed=77)     # odd C, rows not a multiple of any tile
+    o_tab, o_basis = tab.copy(), basis.copy()
+    ost, oit, _ = oracle.solve(o_tab, o_basis, True)
+    st, res, _ = _ffi.solve(tab, basis, True, _ffi.make_opts(writeback_full=True,
+                                                             pivot_variant=variant))
+    assert st == ost and res.iterations == oit and np.array_equal(tab, o_tab)
+
+
+# ------------------------------------------------------------------ degenerate / Bland (config 5)
+def test_beale_cycles_under_reference_rule_and_bland_terminates():
+    g = G.BEALE
+    tab, basis = f64(g["matrix"]), i32(g["basis"])
+    o_tab, o_basis = tab.copy(), basis.copy()
+    ost, oit, otrace = oracle.solve(o_tab, o_basis, True, rule=0, max_iters=300, trace_cap=300)
+    st, res, trace = _ffi.solve(tab.copy(), basis.copy(), True,
+                                _ffi.make_opts(max_iters=300, trace_capacity=300))
+    assert st == ost and res.iterations == oit and trace == otrace
+    o_tab, o_basis = tab.copy(), basis.copy()
+    ost, oit, otrace = oracle.solve(o_tab, o_basis, True, rule=1, max_iters=300, trace_cap=300)
+    st, res, trace = _ffi.solve(tab, basis, True,
+                                _ffi.make_opts(pivot_rule=_ffi.RULE_BLAND, max_iters=300,
+                                               trace_capacity=300, writeback_full=True))
+    assert st == ost == _ffi.OK and trace == otrace and np.array_equal(tab, o_tab)
+    assert abs(res.objective - 0.05) < 1e-12
+
+
+@pytest.mark.parametrize("rule", [0, 1])
+def test_degenerate_lp_basis_bit_exact(rule):
+    """Config 5 at reduced size: exact ratio ties (zero-RHS cone rows, small-integer data)."""
+    tab, basis = synthetic.dense_tableau(128, 128, seed=1234, degenerate=True)
+    o_tab, o_basis = tab.copy(), basis.copy()
+    cap = 20000
+    ost, oit, otrace = oracle.solve(o_tab, o_basis, True, rule=rule, max_iters=cap, trace_cap=cap)
+    st, res, trace = _ffi.solve(tab, basis, True,
+                                _ffi.make_opts(pivot_rule=rule, max_iters=cap, trace_capacity=cap,
+                                               writeback_full=True))
+    assert st == ost and res.iterations == oit
+    assert trace == otrace and np.array_equal(basis, o_basis) and np.array_equal(tab, o_tab)
+
+
+# ------------------------------------------------------------------ two-phase, randomized
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_two_phase_random_matches_oracle(seed):
+    """>= and = rows need artificials (src/simplex.lisp:258-263, 288-325)."""
+    rng = np.random.default_rng(seed)
+    m, n = 40, 30
+    A = rng.integers(1, 9, size=(m, n)).astype(np.float64)
+    x0 = rng.integers(0, 4, size=n).astype(np.float64)
+    kinds = rng.integers(0, 3, size=m)            # 0: <=, 1: >=, 2: =
+    rhs = A @ x0 + np.where(kinds == 0, 5.0, np.where(kinds == 1, -3.0, 0.0))
+    rhs = np.maximum(rhs, 0.0)
+    c = rng.integers(1, 9, size=n).astype(np.float64)
+    n_slack = int((kinds != 2).sum())
+    art_rows = [i for i in range(m) if kinds[i] != 0]
+    C = n + n_slack + 1
+    main = np.zeros((m + 1, C))
+    mb = np.zeros(m, np.int32)
+    off = 0
+    for i in range(m):
+        main[i, :n] = A[i]
+        main[i, -1] = rhs[i]
+        if kinds[i] == 0:
+            main[i, n + off] = 1.0; mb[i] = n + off; off += 1
+        elif kinds[i] == 1:
+            main[i, n + off] = -1.0; mb[i] = C; off += 1
+        else:
+            mb[i] = C
+    main[m, :n] = -c
+    na = len(art_rows)
+    art = np.zeros((m + 1, C + na))
+    ab = mb.copy()
+    art[:m, :C - 1] = main[:m, :C - 1]
+    art[:m, -1] = main[:m, -1]
+    # reference pushes rows, so artificial columns are assigned in reverse row order (:258, 295-299)
+    for k, row in enumerate(reversed(art_rows)):
+        art[row, C - 1 + k] = 1.0
+        ab[row] = C - 1 + k
+    art[m, :C - 1] = art[art_rows][:, :C - 1].sum(axis=0)
+    art[m, -1] = art[art_rows][:, -1].sum()
+    o = [x.copy() for x in (art, ab, main, mb)]
+    ost, oits = oracle.solve_two_phase(*o, True)
+    st, res = _ffi.solve_two_phase(art, ab, main, mb, True, _ffi.make_opts(writeback_full=True))
+    assert st == ost
+    assert (res.iterations_phase1, res.iterations_cleanup, res.iterations) == oits
+    if st == _ffi.OK:
+        assert np.array_equal(main, o[2]) and np.array_equal(mb, o[3])
+        assert np.array_equal(art, o[0]) and np.array_equal(ab, o[1])
+
+
+# ------------------------------------------------------------------ argument errors stay on this side
+def test_invalid_arguments_raise_not_crash():
+    tab, basis = random_tableau(8, 8, seed=1)
+    with _ffi.DeviceTableau(*tab.shape) as d:
+        d.upload(tab, basis)
+        with pytest.raises(_ffi.B200DeviceError):
+            d.pivot(0, 99)
+        with pytest.raises(_ffi.B200DeviceError):
+            d.find_pivoting_row(10 ** 6)
+    with pytest.raises(_ffi.B200DeviceError):
+        _ffi.DeviceTableau(1, 1)
