@@ -364,17 +364,24 @@ static int iterate_locked(b200lp_solver *s, int64_t limit, b200lp_result *out, i
     int slot = 0;
     bool pending[2] = {false, false};
     long long enqueued = 0;
+    bool all_enqueued = false;
     for (;;) {
-        // do not run more than two polls ahead, and never past the cap by more than a batch
-        for (int b = 0; b < batch; ++b) {
-            RC_TRY(enqueue_iteration(s, true, true, time_pivot && s->ev_used < 2 * 8192));
-            ++enqueued;
+        if (!all_enqueued) {
+            // With a cap, limit + 1 iterations decide everything: the extra one lets k_enter
+            // tell "optimal" from "iteration limit".  Without a cap keep the queue one poll ahead.
+            long long nb = batch;
+            if (limit > 0) nb = std::min<long long>(batch, limit + 1 - enqueued);
+            for (long long b = 0; b < nb; ++b) {
+                RC_TRY(enqueue_iteration(s, true, true, time_pivot && s->ev_used < 2 * 8192));
+                ++enqueued;
+            }
+            if (s->shards.size() > 1) CU_TRY(cudaSetDevice(s0.device));
+            CU_TRY(cudaMemcpyAsync(&s0.h_st[slot], s0.st, sizeof(DevState), cudaMemcpyDeviceToHost,
+                                   s0.stream));
+            CU_TRY(cudaEventRecord(s0.ev_poll[slot], s0.stream));
+            pending[slot] = true;
+            if (limit > 0 && enqueued >= limit + 1) all_enqueued = true;
         }
-        if (s->shards.size() > 1) CU_TRY(cudaSetDevice(s0.device));
-        CU_TRY(cudaMemcpyAsync(&s0.h_st[slot], s0.st, sizeof(DevState), cudaMemcpyDeviceToHost,
-                               s0.stream));
-        CU_TRY(cudaEventRecord(s0.ev_poll[slot], s0.stream));
-        pending[slot] = true;
         const int other = slot ^ 1;
         if (pending[other]) {
             CU_TRY(cudaEventSynchronize(s0.ev_poll[other]));
@@ -382,6 +389,7 @@ static int iterate_locked(b200lp_solver *s, int64_t limit, b200lp_result *out, i
             last = s0.h_st[other];
             if (last.status != ST_RUNNING) break;
         }
+        if (all_enqueued) break;   // the newest poll (drained below) is final
         slot = other;
     }
     // drain: the newest poll holds the final state
@@ -440,7 +448,6 @@ static int iterate_locked(b200lp_solver *s, int64_t limit, b200lp_result *out, i
         out->trace_len = tl;
         out->ms_total = now_ms() - t0;
     }
-    (void)enqueued;
     return status;
 }
 

@@ -1,0 +1,64 @@
+"""Row-block sharding on real GPUs (needs >= 2 B200s; skipped otherwise): the pivot sequence and
+every tableau cell must be identical to the 1-GPU / oracle run."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from linear_programming_b200 import _ffi, synthetic
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    try:
+        return _ffi.device_count()
+    except Exception:
+        return 0
+
+
+needs2 = pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+
+
+@needs2
+@pytest.mark.parametrize("ndev,m,n", [(2, 200, 300), (2, 33, 20), (4, 130, 257), (8, 64, 96)])
+def test_in_process_multi_device_bit_exact(ndev, m, n):
+    if _ngpu() < ndev:
+        pytest.skip(f"needs {ndev} GPUs")
+    tab, basis = synthetic.dense_tableau(m, n, seed=13)
+    o_tab, o_basis = tab.copy(), basis.copy()
+    ost, oit, otrace = oracle.solve(o_tab, o_basis, True, trace_cap=1 << 16)
+    st, res, trace = _ffi.solve(tab, basis, True,
+                                _ffi.make_opts(devices=list(range(ndev)), writeback_full=True,
+                                               trace_capacity=1 << 16))
+    assert st == ost and res.iterations == oit and res.n_devices == ndev
+    assert trace == otrace
+    assert np.array_equal(tab, o_tab) and np.array_equal(basis, o_basis)
+
+
+def _torchrun(nproc, *args):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "tests", "sharded_worker.py"), *map(str, args)]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+
+
+@needs2
+@pytest.mark.parametrize("args", [(300, 500), (128, 128, 1, "degenerate"), (128, 128, 0, "degenerate")])
+def test_one_process_per_gpu_nccl(args):
+    out = _torchrun(2, *args)
+    assert out.returncode == 0 and "SHARDED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+@pytest.mark.skipif(_ngpu() < 8, reason="needs 8 GPUs")
+def test_eight_ranks():
+    out = _torchrun(8, 1000, 1500)
+    assert out.returncode == 0 and "SHARDED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
