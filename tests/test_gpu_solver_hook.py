@@ -1,0 +1,33 @@
+"""The reference's solver-level tests (t/simplex.lisp, t/solver.lisp, t/integration.lisp) through
+the `*solver*` hook with the real backend: DSL -> build-tableau -> C ABI -> sm_100a kernels."""
+import pytest
+
+import reference_cases as RC
+from linear_programming_b200 import problem as P, simplex, solver
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", RC.ALL_CASES, ids=lambda c: c.__name__)
+def test_reference_case_on_the_gpu(case):
+    assert solver.SOLVER is simplex.b200_solver
+    case()
+
+
+def test_pivot_row_is_non_destructive():
+    """t/simplex.lisp:135-159"""
+    p = P.make_linear_problem("(max (+ x (* 4 y) (* 3 z)))", *RC.MAIN)
+    t0 = simplex.build_tableau(p, p)
+    t1 = simplex.pivot_row(t0, 0, 0)
+    assert t0.matrix[0].tolist() == [2, 1, 0, 1, 0, 8] and t0.basis_columns.tolist() == [3, 4]
+    assert t1.matrix.tolist() == [[1, .5, 0, .5, 0, 4], [0, 1, 1, 0, 1, 7], [0, -3.5, -3, .5, 0, 4]]
+    assert t1.basis_columns.tolist() == [0, 4] and simplex.tableau_objective_value(t1) == 4
+
+
+def test_backend_keywords():
+    p = P.make_linear_problem("(max (+ x (* 4 y) (* 3 z)))", *RC.MAIN)
+    sol = solver.solve_problem(p, devices=[0], pivot_rule=1)
+    assert solver.solution_objective_value(sol) == 28.5
+    from linear_programming_b200 import conditions
+    with pytest.raises(conditions.SolverError):
+        solver.solve_problem(p, max_iterations=1)
