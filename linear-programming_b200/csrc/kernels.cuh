@@ -341,6 +341,295 @@ k_pivot(double *__restrict__ tab, int64_t ld, int m_local, int R_local, int row0
     }
 }
 
+// ==========================================================================================
+// The pipelined loop (b200lp_iterate / b200lp_solve*): two kernels per iteration, overlapped.
+//
+// The decision chain of an iteration (entering column -> ratio test -> scaled pivot row) needs
+// only O(R + C) cells of the tableau, and every one of them can be computed from the tableau
+// BEFORE the previous pivot's rank-1 update plus that pivot's (column, scaled row):
+//     a'[r,c] = a[r,c] - col[r] * prow[c]        (r != p)         a'[p,c] = prow[c]
+// -- the same rounded product and rounded difference k_update writes, so the bits agree.  Hence
+//     k_look(k -> k+1)  decides iteration k+1 from the tableau S_{k-1} and pivot k's (col, prow)
+//     k_update(k)       streams S_{k-1} -> S_k (out of place, ping-pong buffers)
+// have the same inputs and run CONCURRENTLY on two streams; the latency-bound chain (and, when
+// sharded, the exchange of candidate rows) hides behind the HBM-bound update.  Per-iteration
+// decisions live in a 2-slot ring (slot = k & 1): IterState, colbuf, candidate row, gathered.
+// ==========================================================================================
+constexpr int ST_START = 101;            // ring slot holds no pending pivot (first look of a call)
+constexpr int kLookThreads = 1024;
+
+struct alignas(16) IterState {
+    int status;               // ST_RUNNING: pivot (j, winner of the candidates) is pending
+    int j;                    // entering column
+    int p;                    // leaving row (global); unsharded only, sharded: resolve_winner()
+    int pad;
+    long long iters;          // pivots completed before this iteration
+};
+
+struct alignas(16) Report {   // what the host polls
+    int status;
+    int pad;
+    long long iters;
+};
+
+// Pick the global leaving row from the candidate headers (one per rank; stride in doubles).
+// Same (ratio, key) lexicographic minimum on every rank == the unsharded first-index scan.
+__device__ __forceinline__ Cand resolve_winner(const double *cand_base, int64_t stride, int world,
+                                               int *winner)
+{
+    Cand best;
+    best.q = 0.0; best.key = 0; best.row = -1;
+    int w = 0;
+    for (int g = 0; g < world; ++g) {
+        const CandHdr *h = reinterpret_cast<const CandHdr *>(cand_base + g * stride);
+        Cand c;
+        c.q = h->q; c.key = (int)h->key; c.row = (int)h->row;
+        const Cand nb = cand_min(best, c);
+        if (nb.row != best.row) { best = nb; w = g; }
+    }
+    *winner = w;
+    return best;
+}
+
+struct LookArgs {
+    const double *src;        // tableau S_{k-1}: this shard's block, R_local x ld
+    int64_t ld;
+    int C, m_local, R_local, row0, world;
+    int is_max, rule;
+    double thr_enter, thr_pivot;
+    long long max_iters;      // 0 = unlimited
+    const IterState *st_in;   // ring slot of pending iteration k
+    IterState *st_out;        // ring slot of iteration k+1
+    const double *col_in;     // pivot column of iteration k (R_local)
+    double *col_out;          // pivot column of iteration k+1
+    const double *cand_in;    // candidates of iteration k: world x (hdr + ld) (own only if world == 1)
+    int64_t cand_stride;
+    double *cand_out;         // this shard's candidate for iteration k+1: hdr + ld
+    int32_t *basis;
+    Report *report;
+    int2 *trace;
+    int trace_cap;
+};
+
+// k_look: find-entering-column + find-pivoting-row + the division half of n-pivot-row
+// (src/simplex.lisp:362-389, 344-348) for iteration k+1, evaluated on the not-yet-updated
+// tableau.  It also retires iteration k: basis[p] <- j (:358), pivot trace, iteration count,
+// and (sharded) the UNBOUNDED verdict that is only known after the exchange.  One CTA.
+__global__ void __launch_bounds__(kLookThreads) k_look(const LookArgs A)
+{
+    __shared__ Cand red[kLookThreads / 32];
+    __shared__ Cand s_win;
+    __shared__ int s_w;
+    const IterState st = *A.st_in;
+    const int tid = threadIdx.x;
+    if (st.status != ST_RUNNING && st.status != ST_START) {   // solve already over: pass it on
+        if (tid == 0) *A.st_out = st;
+        return;
+    }
+    const bool pending = st.status == ST_RUNNING;
+    long long iters = st.iters;
+    int p_local = -1;
+    const double *prow = nullptr;
+    if (pending) {
+        if (tid == 0) {
+            int w = 0;
+            Cand win;
+            if (A.world == 1) {
+                win.q = 0.0; win.key = 0; win.row = st.p;
+            } else {
+                win = resolve_winner(A.cand_in, A.cand_stride, A.world, &w);
+            }
+            s_win = win;
+            s_w = w;
+        }
+        __syncthreads();
+        const int p = s_win.row;
+        if (p < 0) {                                           // no rank had an eligible row
+            if (tid == 0) {
+                IterState o = st;
+                o.status = ST_UNBOUNDED;
+                *A.st_out = o;
+                A.report->iters = iters;
+                A.report->status = ST_UNBOUNDED;
+            }
+            return;
+        }
+        prow = A.cand_in + (int64_t)s_w * A.cand_stride + kCandHdr;
+        const int rel = p - A.row0;
+        if (rel >= 0 && rel < A.m_local) p_local = rel;
+        if (tid == 0) {
+            if (p_local >= 0) A.basis[p_local] = st.j;         // (setf (aref basis p) j) :358
+            if (A.trace && iters < A.trace_cap) A.trace[iters] = make_int2(st.j, p);
+        }
+        iters += 1;
+        __syncthreads();                                       // basis[] visible to the Bland keys
+    }
+    const double *col = A.col_in;
+    const int nv = A.C - 1;
+
+    // ---- stage 1: entering column over the (updated) objective row ---------------------------
+    const double *obj = A.src + (int64_t)A.m_local * A.ld;
+    const double t_obj = pending ? col[A.m_local] : 0.0;
+    Cand best;
+    best.q = 0.0; best.key = 0; best.row = -1;
+    if (A.rule == 0) {
+        for (int c = tid; c < nv; c += kLookThreads) {
+            double v = obj[c];
+            if (pending) v = __dsub_rn(v, __dmul_rn(t_obj, prow[c]));
+            const double k = A.is_max ? v : -v;
+            if (best.row < 0 || k < best.q) { best.q = k; best.key = c; best.row = c; }
+        }
+    } else {
+        for (int c = tid; c < nv; c += kLookThreads) {
+            double v = obj[c];
+            if (pending) v = __dsub_rn(v, __dmul_rn(t_obj, prow[c]));
+            const double k = A.is_max ? v : -v;
+            if (k < 0.0 - A.thr_enter) { best.q = 0.0; best.key = c; best.row = c; break; }
+        }
+    }
+    best = cand_block_min<kLookThreads>(best, red);
+    {
+        const bool accept = (best.row >= 0) && (A.rule != 0 || best.q < 0.0 - A.thr_enter);
+        int fin = ST_RUNNING;
+        if (!accept) fin = ST_OPTIMAL;
+        else if (A.max_iters > 0 && iters >= A.max_iters) fin = ST_ITERATION_LIMIT;
+        if (fin != ST_RUNNING) {
+            if (tid == 0) {
+                IterState o;
+                o.status = fin; o.j = accept ? best.row : -1; o.p = -1; o.pad = 0; o.iters = iters;
+                *A.st_out = o;
+                A.report->iters = iters;
+                A.report->status = fin;
+            }
+            return;
+        }
+    }
+    const int j = best.row;
+
+    // ---- stage 2: pivot-column snapshot + ratio test over this shard's rows --------------------
+    const int rhs = A.C - 1;
+    const double pj = pending ? prow[j] : 0.0;
+    const double pb = pending ? prow[rhs] : 0.0;
+    Cand c;
+    c.q = 0.0; c.key = 0; c.row = -1;
+    for (int i = tid; i < A.R_local; i += kLookThreads) {
+        const double *rowp = A.src + (int64_t)i * A.ld;
+        double a = rowp[j];
+        double t = 0.0;
+        if (pending) {
+            t = col[i];
+            a = (i == p_local) ? pj : __dsub_rn(a, __dmul_rn(t, pj));
+        }
+        A.col_out[i] = a;
+        if (i < A.m_local && 0.0 + A.thr_pivot < a) {
+            double b = rowp[rhs];
+            if (pending) b = (i == p_local) ? pb : __dsub_rn(b, __dmul_rn(t, pb));
+            Cand d;
+            d.q = __ddiv_rn(b, a);
+            d.key = A.rule ? A.basis[i] : A.row0 + i;
+            d.row = A.row0 + i;
+            c = cand_min(c, d);
+        }
+    }
+    __syncthreads();                                           // red[] reuse
+    c = cand_block_min<kLookThreads>(c, red);
+
+    // ---- stage 3: this shard's candidate row / its pivot element -------------------------------
+    CandHdr *hdr = reinterpret_cast<CandHdr *>(A.cand_out);
+    if (c.row >= 0) {
+        const int i = c.row - A.row0;
+        const double s = A.col_out[i];                         // written above, synced by the reduce
+        const double t = pending ? col[i] : 0.0;
+        const bool is_p = (i == p_local);
+        const double *rowp = A.src + (int64_t)i * A.ld;
+        double *out = A.cand_out + kCandHdr;
+        for (int cc = tid; cc < (int)A.ld; cc += kLookThreads) {
+            double v = 0.0;
+            if (cc < A.C) {
+                v = rowp[cc];
+                if (pending) v = is_p ? prow[cc] : __dsub_rn(v, __dmul_rn(t, prow[cc]));
+                v = __ddiv_rn(v, s);
+            }
+            out[cc] = v;
+        }
+    }
+    if (tid == 0) {
+        hdr->q = c.q; hdr->key = c.key; hdr->row = c.row; hdr->pad = 0;
+        IterState o;
+        o.status = ST_RUNNING; o.j = j; o.p = c.row; o.pad = 0; o.iters = iters;
+        if (A.world == 1 && c.row < 0) {
+            o.status = ST_UNBOUNDED;
+            A.report->iters = iters;
+            A.report->status = ST_UNBOUNDED;
+        }
+        *A.st_out = o;
+    }
+}
+
+// k_update: the rank-1 update of iteration k, streaming src -> dst (dst may equal src).
+// Same tiling as k_pivot; reads its decisions from the ring slot and never writes state.
+template <int TR, int UNROLL, int VEC, bool STREAM>
+__global__ void __launch_bounds__(kPivotThreads)
+k_update(const double *src, double *dst, int64_t ld, int m_local, int R_local, int row0, int world,
+         const IterState *__restrict__ st, const double *__restrict__ colbuf,
+         const double *__restrict__ cand_base, int64_t cand_stride)
+{
+    if (st->status != ST_RUNNING) return;
+    __shared__ double s_col[TR];
+    __shared__ int s_p, s_w;
+    if (threadIdx.x == 0) {
+        int w = 0, p = st->p;
+        if (world > 1) p = resolve_winner(cand_base, cand_stride, world, &w).row;
+        s_p = p; s_w = w;
+    }
+    const int ldv = (int)(ld >> 1);
+    const int r_begin = blockIdx.y * TR;
+    const int r_end = min(R_local, r_begin + TR);
+    for (int t = threadIdx.x; t < TR; t += kPivotThreads)
+        s_col[t] = (r_begin + t < r_end) ? colbuf[r_begin + t] : 0.0;
+    __syncthreads();
+    if (s_p < 0) return;                                       // unbounded: nothing to apply
+    const int p_rel = s_p - row0;
+    const int p_local = (p_rel >= 0 && p_rel < m_local) ? p_rel : -1;
+    const double2 *prow2 =
+        reinterpret_cast<const double2 *>(cand_base + (int64_t)s_w * cand_stride + kCandHdr);
+    int cv[VEC];
+    double2 pr[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        cv[v] = (blockIdx.x * VEC + v) * kPivotThreads + threadIdx.x;
+        pr[v] = (cv[v] < ldv) ? prow2[cv[v]] : make_double2(0.0, 0.0);
+    }
+    const double2 *src2 = reinterpret_cast<const double2 *>(src);
+    double2 *dst2 = reinterpret_cast<double2 *>(dst);
+    for (int r = r_begin; r < r_end; r += UNROLL) {
+        double2 a[UNROLL][VEC];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+                if (r + u < r_end && cv[v] < ldv)
+                    a[u][v] = ld_tab<STREAM>(src2 + (int64_t)(r + u) * ldv + cv[v]);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if (r + u < r_end) {
+                const double t = s_col[r + u - r_begin];
+                const bool is_p = (r + u == p_local);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    if (cv[v] < ldv) {
+                        double2 o;
+                        o.x = __dsub_rn(a[u][v].x, __dmul_rn(t, pr[v].x));
+                        o.y = __dsub_rn(a[u][v].y, __dmul_rn(t, pr[v].y));
+                        if (is_p) o = pr[v];
+                        st_tab<STREAM>(dst2 + (int64_t)(r + u) * ldv + cv[v], o);
+                    }
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Small helpers for the boundary: gather the RHS column into a contiguous buffer (what
 // tableau-variable reads, src/simplex.lisp:81-107) and the two-phase transition pieces.

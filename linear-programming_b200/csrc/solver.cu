@@ -80,12 +80,25 @@ struct Shard {
     int m_local = 0;            // constraint rows owned
     int R_local = 0;            // m_local + 1 (objective replica last)
     int64_t ld = 0;             // device leading dimension (multiple of 16 doubles)
-    cudaStream_t stream = nullptr;
-    double *tab = nullptr;
+    cudaStream_t stream = nullptr;      // uploads, step-by-step API, k_update
+    cudaStream_t look_stream = nullptr; // k_look + candidate exchange (high priority)
+    double *tabs[2] = {nullptr, nullptr}; // ping-pong tableau buffers; [1] allocated on first iterate
+    int cur = 0;                // which buffer holds the current tableau
+    double *tab = nullptr;      // == tabs[cur]
     int32_t *basis = nullptr;
-    double *colbuf = nullptr;
-    double *cand = nullptr;     // CandHdr + ld doubles
-    double *gathered = nullptr; // world * (kCandHdr + ld) doubles (sharded only)
+    // 2-slot decision ring of the pipelined loop (slot = iteration & 1); the step-by-step API
+    // uses slot 0 through the aliases below
+    double *colring[2] = {nullptr, nullptr};
+    double *candring[2] = {nullptr, nullptr};
+    double *gathring[2] = {nullptr, nullptr};
+    IterState *ring = nullptr;  // 2 slots
+    Report *report = nullptr;
+    Report *h_report = nullptr; // pinned, 2 slots
+    cudaEvent_t ev_look[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_upd[4] = {nullptr, nullptr, nullptr, nullptr};
+    double *colbuf = nullptr;   // == colring[0]
+    double *cand = nullptr;     // == candring[0]: CandHdr + ld doubles
+    double *gathered = nullptr; // == gathring[0]: world * (kCandHdr + ld) doubles (sharded only)
     double *colout = nullptr;   // R_local doubles, RHS gather
     DevState *st = nullptr;
     Cand *partials = nullptr;
@@ -128,18 +141,35 @@ static void fill_thresholds(b200lp_solver *s)
 static int alloc_shard(b200lp_solver *s, Shard &sh)
 {
     CU_TRY(cudaSetDevice(sh.device));
-    CU_TRY(cudaStreamCreateWithFlags(&sh.stream, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    CU_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CU_TRY(cudaStreamCreateWithPriority(&sh.stream, cudaStreamNonBlocking, prio_lo));
+    CU_TRY(cudaStreamCreateWithPriority(&sh.look_stream, cudaStreamNonBlocking, prio_hi));
     sh.ld = round_up(s->C, 16);
     const int64_t stride = kCandHdr + sh.ld;
-    CU_TRY(cudaMalloc(&sh.tab, sizeof(double) * sh.ld * sh.R_local));
+    CU_TRY(cudaMalloc(&sh.tabs[0], sizeof(double) * sh.ld * sh.R_local));
+    sh.cur = 0;
+    sh.tab = sh.tabs[0];
     CU_TRY(cudaMalloc(&sh.basis, sizeof(int32_t) * std::max(1, sh.m_local)));
-    CU_TRY(cudaMalloc(&sh.colbuf, sizeof(double) * sh.R_local));
     CU_TRY(cudaMalloc(&sh.colout, sizeof(double) * sh.R_local));
-    CU_TRY(cudaMalloc(&sh.cand, sizeof(double) * stride));
-    CU_TRY(cudaMemsetAsync(sh.cand, 0, sizeof(double) * stride, sh.stream));
-    if (s->world > 1) {
-        CU_TRY(cudaMalloc(&sh.gathered, sizeof(double) * stride * s->world));
-        CU_TRY(cudaMemsetAsync(sh.gathered, 0, sizeof(double) * stride * s->world, sh.stream));
+    for (int k = 0; k < 2; ++k) {
+        CU_TRY(cudaMalloc(&sh.colring[k], sizeof(double) * sh.R_local));
+        CU_TRY(cudaMalloc(&sh.candring[k], sizeof(double) * stride));
+        CU_TRY(cudaMemsetAsync(sh.candring[k], 0, sizeof(double) * stride, sh.stream));
+        if (s->world > 1) {
+            CU_TRY(cudaMalloc(&sh.gathring[k], sizeof(double) * stride * s->world));
+            CU_TRY(cudaMemsetAsync(sh.gathring[k], 0, sizeof(double) * stride * s->world, sh.stream));
+        }
+    }
+    sh.colbuf = sh.colring[0];
+    sh.cand = sh.candring[0];
+    sh.gathered = sh.gathring[0];
+    CU_TRY(cudaMalloc(&sh.ring, 2 * sizeof(IterState)));
+    CU_TRY(cudaMalloc(&sh.report, sizeof(Report)));
+    CU_TRY(cudaMallocHost(&sh.h_report, 2 * sizeof(Report)));
+    for (int k = 0; k < 4; ++k) {
+        CU_TRY(cudaEventCreateWithFlags(&sh.ev_look[k], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&sh.ev_upd[k], cudaEventDisableTiming));
     }
     sh.ratio_blocks = (sh.R_local + kRatioThreads - 1) / kRatioThreads;
     CU_TRY(cudaMalloc(&sh.partials, sizeof(Cand) * sh.ratio_blocks));
@@ -163,10 +193,21 @@ static void free_shard(Shard &sh)
 {
     cudaSetDevice(sh.device);
     if (sh.stream) cudaStreamSynchronize(sh.stream);
+    if (sh.look_stream) cudaStreamSynchronize(sh.look_stream);
     if (sh.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(sh.comm);
-    cudaFree(sh.tab); cudaFree(sh.basis); cudaFree(sh.colbuf); cudaFree(sh.colout);
-    cudaFree(sh.cand); cudaFree(sh.gathered); cudaFree(sh.partials); cudaFree(sh.st);
+    cudaFree(sh.tabs[0]); cudaFree(sh.tabs[1]); cudaFree(sh.basis); cudaFree(sh.colout);
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(sh.colring[k]); cudaFree(sh.candring[k]); cudaFree(sh.gathring[k]);
+    }
+    cudaFree(sh.ring); cudaFree(sh.report);
+    cudaFree(sh.partials); cudaFree(sh.st);
     cudaFree(sh.trace);
+    if (sh.h_report) cudaFreeHost(sh.h_report);
+    for (int k = 0; k < 4; ++k) {
+        if (sh.ev_look[k]) cudaEventDestroy(sh.ev_look[k]);
+        if (sh.ev_upd[k]) cudaEventDestroy(sh.ev_upd[k]);
+    }
+    if (sh.look_stream) cudaStreamDestroy(sh.look_stream);
     if (sh.h_st) cudaFreeHost(sh.h_st);
     if (sh.h_trace) cudaFreeHost(sh.h_trace);
     for (cudaEvent_t e : sh.ev_pivot) cudaEventDestroy(e);
@@ -282,14 +323,17 @@ static void launch_pivot(b200lp_solver *s, Shard &sh)
     s->kernel_launches++;
 }
 
-static int exchange(b200lp_solver *s)
+// All-gather of every shard's candidate (header + scaled row) of ring slot `slot`.  The pipelined
+// loop runs it on the look stream, the step-by-step API (slot 0) on the main stream.
+static int exchange(b200lp_solver *s, int slot = 0, bool on_look_stream = false)
 {
     if (s->world == 1) return B200LP_OK;
     const size_t bytes = sizeof(double) * (kCandHdr + s->shards[0].ld);
     if (s->shards.size() > 1) NCCL_TRY(g_nccl.GroupStart());
     for (Shard &sh : s->shards) {
         if (s->shards.size() > 1) cudaSetDevice(sh.device);
-        NCCL_TRY(g_nccl.AllGather(sh.cand, sh.gathered, bytes, ncclChar, sh.comm, sh.stream));
+        NCCL_TRY(g_nccl.AllGather(sh.candring[slot], sh.gathring[slot], bytes, ncclChar, sh.comm,
+                                  on_look_stream ? sh.look_stream : sh.stream));
     }
     if (s->shards.size() > 1) NCCL_TRY(g_nccl.GroupEnd());
     return B200LP_OK;
@@ -335,6 +379,113 @@ static int enqueue_iteration(b200lp_solver *s, bool do_enter, bool with_trace, b
     return B200LP_OK;
 }
 
+// ---- pipelined loop: k_look(k -> k+1) on the look stream, k_update(k) on the main stream -----
+static void launch_look(b200lp_solver *s, Shard &sh, long long k, long long cap)
+{
+    const int in = (int)(k & 1), out = in ^ 1;
+    LookArgs a;
+    // look(k -> k+1) reads the tableau before pivot k: buffer cur + (k-1) (cur itself for k = 0)
+    a.src = sh.tabs[(sh.cur + (int)((k > 0 ? k - 1 : 0) & 1)) & 1];
+    a.ld = sh.ld;
+    a.C = (int)s->C; a.m_local = sh.m_local; a.R_local = sh.R_local; a.row0 = (int)sh.row0;
+    a.world = s->world; a.is_max = s->is_max; a.rule = s->opts.pivot_rule;
+    a.thr_enter = s->thr_enter; a.thr_pivot = s->thr_pivot;
+    a.max_iters = cap;
+    a.st_in = sh.ring + in; a.st_out = sh.ring + out;
+    a.col_in = sh.colring[in]; a.col_out = sh.colring[out];
+    a.cand_in = s->world > 1 ? sh.gathring[in] : sh.candring[in];
+    a.cand_stride = kCandHdr + sh.ld;
+    a.cand_out = sh.candring[out];
+    a.basis = sh.basis; a.report = sh.report;
+    a.trace = sh.trace; a.trace_cap = s->opts.trace_capacity;
+    k_look<<<1, kLookThreads, 0, sh.look_stream>>>(a);
+    s->kernel_launches++;
+}
+
+template <int TR, int UNROLL, int VEC, bool STREAM>
+static void launch_update_t(b200lp_solver *s, Shard &sh, long long k)
+{
+    const int slot = (int)(k & 1);
+    const double *src = sh.tabs[(sh.cur + (int)((k - 1) & 1)) & 1];
+    double *dst = sh.tabs[(sh.cur + (int)(k & 1)) & 1];
+    const int ldv = (int)(sh.ld / 2);
+    dim3 grid((ldv + kPivotThreads * VEC - 1) / (kPivotThreads * VEC), (sh.R_local + TR - 1) / TR);
+    k_update<TR, UNROLL, VEC, STREAM><<<grid, kPivotThreads, 0, sh.stream>>>(
+        src, dst, sh.ld, sh.m_local, sh.R_local, (int)sh.row0, s->world, sh.ring + slot,
+        sh.colring[slot], s->world > 1 ? sh.gathring[slot] : sh.candring[slot], kCandHdr + sh.ld);
+}
+
+static void launch_update(b200lp_solver *s, Shard &sh, long long k)
+{
+    int v = s->opts.pivot_variant;
+    if (v == 0) {
+        // Tableaus that fit the 126 MB L2 keep default caching; larger ones stream with the
+        // deepest load batch (16 rows in flight per thread: best on B200 at every size > L2,
+        // profiles/r01_variant_sweep_*.json).
+        const double bytes = 8.0 * (double)sh.ld * sh.R_local;
+        v = bytes > 48e6 ? 6 : 2;
+    }
+    switch (v) {
+    default:
+    case 1: launch_update_t<64, 8, 1, true>(s, sh, k); break;
+    case 2: launch_update_t<64, 8, 1, false>(s, sh, k); break;
+    case 3: launch_update_t<128, 8, 1, true>(s, sh, k); break;
+    case 4: launch_update_t<64, 4, 2, true>(s, sh, k); break;
+    case 5: launch_update_t<32, 8, 1, true>(s, sh, k); break;
+    case 6: launch_update_t<64, 16, 1, true>(s, sh, k); break;
+    case 7: launch_update_t<128, 8, 2, true>(s, sh, k); break;
+    case 8: launch_update_t<64, 4, 1, true>(s, sh, k); break;
+    case 9: launch_update_t<128, 16, 1, false>(s, sh, k); break;
+    }
+    s->kernel_launches++;
+}
+
+// look(k -> k+1) (+ exchange of its candidates) on every local shard; it may start once
+// update(k-1) has produced the tableau it reads.
+static int enqueue_look(b200lp_solver *s, long long k, long long cap)
+{
+    const bool multi = s->shards.size() > 1;
+    for (Shard &sh : s->shards) {
+        if (multi) CU_TRY(cudaSetDevice(sh.device));
+        if (k > 1) CU_TRY(cudaStreamWaitEvent(sh.look_stream, sh.ev_upd[(k - 1) & 3], 0));
+        launch_look(s, sh, k, cap);
+    }
+    RC_TRY(exchange(s, (int)((k + 1) & 1), true));
+    for (Shard &sh : s->shards) {
+        if (multi) CU_TRY(cudaSetDevice(sh.device));
+        CU_TRY(cudaEventRecord(sh.ev_look[(k + 1) & 3], sh.look_stream));
+    }
+    return B200LP_OK;
+}
+
+// update(k) on every local shard, after look(k-1 -> k) (+ exchange) has decided it.
+static int enqueue_update(b200lp_solver *s, long long k, bool time_pivot)
+{
+    const bool multi = s->shards.size() > 1;
+    for (Shard &sh : s->shards) {
+        if (multi) CU_TRY(cudaSetDevice(sh.device));
+        CU_TRY(cudaStreamWaitEvent(sh.stream, sh.ev_look[k & 3], 0));
+        const bool timed = time_pivot && &sh == &s->shards[0];
+        if (timed) {
+            if (sh.ev_pivot.size() < s->ev_used + 2) {
+                cudaEvent_t a, b;
+                CU_TRY(cudaEventCreate(&a));
+                CU_TRY(cudaEventCreate(&b));
+                sh.ev_pivot.push_back(a);
+                sh.ev_pivot.push_back(b);
+            }
+            CU_TRY(cudaEventRecord(sh.ev_pivot[s->ev_used], sh.stream));
+        }
+        launch_update(s, sh, k);
+        if (timed) {
+            CU_TRY(cudaEventRecord(sh.ev_pivot[s->ev_used + 1], sh.stream));
+            s->ev_used += 2;
+        }
+        CU_TRY(cudaEventRecord(sh.ev_upd[k & 3], sh.stream));
+    }
+    return B200LP_OK;
+}
+
 static int default_poll_interval(const b200lp_solver *s)
 {
     if (s->opts.poll_interval > 0) return s->opts.poll_interval;
@@ -342,6 +493,8 @@ static int default_poll_interval(const b200lp_solver *s)
 }
 
 // n-solve-tableau's loop, src/simplex.lisp:455-460, for at most `limit` more pivots.
+// Iteration k = { update(k) on the main stream || look(k -> k+1) on the look stream }; the host
+// enqueues a batch ahead and polls the device Report one batch behind, so neither stream drains.
 static int iterate_locked(b200lp_solver *s, int64_t limit, b200lp_result *out, int32_t *trace_j,
                           int32_t *trace_r)
 {
@@ -351,77 +504,103 @@ static int iterate_locked(b200lp_solver *s, int64_t limit, b200lp_result *out, i
     const long long cap = limit > 0 ? start_iters + limit : 0;
     const int64_t launches0 = s->kernel_launches;
     s->ev_used = 0;
-    RC_TRY(push_state(s, ST_RUNNING, cap, -1, -1));
+    for (Shard &sh : s->shards) {
+        CU_TRY(cudaSetDevice(sh.device));
+        if (!sh.tabs[1]) CU_TRY(cudaMalloc(&sh.tabs[1], sizeof(double) * sh.ld * sh.R_local));
+        IterState init;
+        std::memset(&init, 0, sizeof(init));
+        init.status = ST_START; init.j = -1; init.p = -1; init.iters = start_iters;
+        Report rep;
+        rep.status = ST_RUNNING; rep.pad = 0; rep.iters = start_iters;
+        CU_TRY(cudaMemcpyAsync(sh.ring, &init, sizeof(init), cudaMemcpyHostToDevice, sh.look_stream));
+        CU_TRY(cudaMemcpyAsync(sh.report, &rep, sizeof(rep), cudaMemcpyHostToDevice, sh.look_stream));
+        CU_TRY(cudaStreamSynchronize(sh.look_stream));
+        CU_TRY(cudaStreamSynchronize(sh.stream));
+    }
     const bool time_pivot = s->opts.time_kernels != 0;
     const int batch = default_poll_interval(s);
     Shard &s0 = s->shards[0];
     CU_TRY(cudaSetDevice(s0.device));
     CU_TRY(cudaEventRecord(s0.ev_begin, s0.stream));
+    RC_TRY(enqueue_look(s, 0, cap));                       // decides iteration 1
 
-    DevState last;
-    std::memset(&last, 0, sizeof(last));
-    last.status = ST_RUNNING;
+    Report last;
+    last.status = ST_RUNNING; last.pad = 0; last.iters = start_iters;
     int slot = 0;
     bool pending[2] = {false, false};
-    long long enqueued = 0;
+    long long k = 0;                                       // iterations enqueued
     bool all_enqueued = false;
     for (;;) {
         if (!all_enqueued) {
-            // With a cap, limit + 1 iterations decide everything: the extra one lets k_enter
-            // tell "optimal" from "iteration limit".  Without a cap keep the queue one poll ahead.
+            // With a cap, `limit` iterations decide everything: look(limit -> limit+1) tells
+            // "optimal" from "iteration limit".  Without a cap keep the queue one poll ahead.
             long long nb = batch;
-            if (limit > 0) nb = std::min<long long>(batch, limit + 1 - enqueued);
+            if (limit > 0) nb = std::min<long long>(batch, limit - k);
             for (long long b = 0; b < nb; ++b) {
-                RC_TRY(enqueue_iteration(s, true, true, time_pivot && s->ev_used < 2 * 8192));
-                ++enqueued;
+                ++k;
+                RC_TRY(enqueue_update(s, k, time_pivot && s->ev_used < 2 * 8192));
+                RC_TRY(enqueue_look(s, k, cap));
             }
             if (s->shards.size() > 1) CU_TRY(cudaSetDevice(s0.device));
-            CU_TRY(cudaMemcpyAsync(&s0.h_st[slot], s0.st, sizeof(DevState), cudaMemcpyDeviceToHost,
-                                   s0.stream));
-            CU_TRY(cudaEventRecord(s0.ev_poll[slot], s0.stream));
+            CU_TRY(cudaMemcpyAsync(&s0.h_report[slot], s0.report, sizeof(Report),
+                                   cudaMemcpyDeviceToHost, s0.look_stream));
+            CU_TRY(cudaEventRecord(s0.ev_poll[slot], s0.look_stream));
             pending[slot] = true;
-            if (limit > 0 && enqueued >= limit + 1) all_enqueued = true;
+            if (limit > 0 && k >= limit) all_enqueued = true;
         }
         const int other = slot ^ 1;
         if (pending[other]) {
             CU_TRY(cudaEventSynchronize(s0.ev_poll[other]));
             pending[other] = false;
-            last = s0.h_st[other];
+            last = s0.h_report[other];
             if (last.status != ST_RUNNING) break;
         }
         if (all_enqueued) break;   // the newest poll (drained below) is final
         slot = other;
     }
     // drain: the newest poll holds the final state
-    for (int k = 0; k < 2; ++k) {
-        if (pending[k]) {
-            CU_TRY(cudaEventSynchronize(s0.ev_poll[k]));
-            if (s0.h_st[k].iters >= last.iters) last = s0.h_st[k];
+    for (int q = 0; q < 2; ++q) {
+        if (pending[q]) {
+            CU_TRY(cudaEventSynchronize(s0.ev_poll[q]));
+            if (last.status == ST_RUNNING) last = s0.h_report[q];
         }
     }
+    CU_TRY(cudaGetLastError());
+    for (Shard &sh : s->shards) {
+        CU_TRY(cudaSetDevice(sh.device));
+        CU_TRY(cudaStreamSynchronize(sh.look_stream));
+    }
+    CU_TRY(cudaSetDevice(s0.device));
     CU_TRY(cudaEventRecord(s0.ev_end, s0.stream));
     for (Shard &sh : s->shards) {
         CU_TRY(cudaSetDevice(sh.device));
         CU_TRY(cudaStreamSynchronize(sh.stream));
     }
     CU_TRY(cudaSetDevice(s0.device));
+    if (last.status == ST_RUNNING)
+        return fail(B200LP_ERR_INTERNAL, "iterate", "device loop ended without a verdict");
+    const long long done = last.iters - start_iters;
     s->iters_done = last.iters;
+    for (Shard &sh : s->shards) {                          // pivots ping-pong between the buffers
+        sh.cur = (sh.cur + (int)(done & 1)) & 1;
+        sh.tab = sh.tabs[sh.cur];
+    }
     const int status = last.status;
 
     if (out) {
         std::memset(out, 0, sizeof(*out));
         out->status = status;
         out->n_devices = s->world;
-        out->iterations = s->iters_done - start_iters;
+        out->iterations = done;
         float ms = 0.f;
         CU_TRY(cudaEventElapsedTime(&ms, s0.ev_begin, s0.ev_end));
         out->ms_solve = ms;
         double pk = 0.0;
         // only launches that did real work: the first `iterations` timed pairs
         const size_t real = (size_t)std::min<long long>(out->iterations, (long long)(s->ev_used / 2));
-        for (size_t k = 0; k < real; ++k) {
+        for (size_t q = 0; q < real; ++q) {
             float e = 0.f;
-            CU_TRY(cudaEventElapsedTime(&e, s0.ev_pivot[2 * k], s0.ev_pivot[2 * k + 1]));
+            CU_TRY(cudaEventElapsedTime(&e, s0.ev_pivot[2 * q], s0.ev_pivot[2 * q + 1]));
             pk += e;
         }
         out->ms_pivot_kernel = pk;
@@ -438,9 +617,9 @@ static int iterate_locked(b200lp_solver *s, int64_t limit, b200lp_result *out, i
             tl = (int)std::min<long long>(s->iters_done, s->opts.trace_capacity);
             if (tl > 0 && (trace_j || trace_r)) {
                 CU_TRY(cudaMemcpy(s0.h_trace, s0.trace, sizeof(int2) * tl, cudaMemcpyDeviceToHost));
-                for (int k = 0; k < tl; ++k) {
-                    if (trace_j) trace_j[k] = s0.h_trace[k].x;
-                    if (trace_r) trace_r[k] = s0.h_trace[k].y;
+                for (int q = 0; q < tl; ++q) {
+                    if (trace_j) trace_j[q] = s0.h_trace[q].x;
+                    if (trace_r) trace_r[q] = s0.h_trace[q].y;
                 }
                 out->d2h_bytes += sizeof(int2) * tl;
             }
