@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200LP_VERSION 100 /* 0.1.0 */
+#define B200LP_VERSION 101 /* 0.1.1 */
 #define B200LP_MAX_DEVICES 8
 
 /* ---- status codes --------------------------------------------------------------------------
@@ -45,7 +45,8 @@ enum {
     B200LP_ERR_NCCL = -3,
     B200LP_ERR_NO_DEVICE = -4,
     B200LP_ERR_OUT_OF_MEMORY = -5,
-    B200LP_ERR_INTERNAL = -6
+    B200LP_ERR_INTERNAL = -6,
+    B200LP_ERR_PEER_TIMEOUT = -7  /* sharded: a peer GPU's candidate row never arrived            */
 };
 
 enum { B200LP_RULE_REFERENCE = 0, /* Dantzig, first index on ties: src/simplex.lisp:362-389      */
@@ -85,7 +86,10 @@ typedef struct b200lp_result {
     int64_t d2h_bytes;
     int64_t bytes_per_pivot;     /* algorithmic: 16 * R * C, per device: 16*R_local*C   */
     int32_t trace_len;           /* entries valid in the trace buffers                              */
-    int32_t reserved;
+    int32_t exchange_mode;       /* sharded candidates: 0 one shard, 1 NCCL all-gather, 2 peer-mapped */
+    double  ms_look_kernel;      /* sum of lookahead-kernel durations (time_kernels only)           */
+    double  ms_exchange;         /* sum of candidate-exchange durations (time_kernels, sharded)     */
+    int64_t look_kernel_launches;
 } b200lp_result;
 
 /* ---- one-shot calls: what the `*solver*` backend function uses ------------------------------

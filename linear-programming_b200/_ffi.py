@@ -17,6 +17,7 @@ MAX_DEVICES = 8
 OK, UNBOUNDED, INFEASIBLE, ITERATION_LIMIT, ARTIFICIAL_STUCK = 0, 1, 2, 3, 4
 ERR_INVALID_ARG, ERR_CUDA, ERR_NCCL, ERR_NO_DEVICE, ERR_OUT_OF_MEMORY, ERR_INTERNAL = \
     -1, -2, -3, -4, -5, -6
+ERR_PEER_TIMEOUT = -7
 RULE_REFERENCE, RULE_BLAND = 0, 1
 
 
@@ -67,11 +68,14 @@ class Result(ctypes.Structure):
         ("d2h_bytes", ctypes.c_int64),
         ("bytes_per_pivot", ctypes.c_int64),
         ("trace_len", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("exchange_mode", ctypes.c_int32),
+        ("ms_look_kernel", ctypes.c_double),
+        ("ms_exchange", ctypes.c_double),
+        ("look_kernel_launches", ctypes.c_int64),
     ]
 
     def as_dict(self):
-        return {name: getattr(self, name) for name, _ in self._fields_ if name != "reserved"}
+        return {name: getattr(self, name) for name, _ in self._fields_}
 
 
 _dp = ctypes.POINTER(ctypes.c_double)

@@ -342,28 +342,42 @@ k_pivot(double *__restrict__ tab, int64_t ld, int m_local, int R_local, int row0
 }
 
 // ==========================================================================================
-// The pipelined loop (b200lp_iterate / b200lp_solve*): two kernels per iteration, overlapped.
+// The pipelined loop (b200lp_iterate / b200lp_solve*).
 //
 // The decision chain of an iteration (entering column -> ratio test -> scaled pivot row) needs
 // only O(R + C) cells of the tableau, and every one of them can be computed from the tableau
 // BEFORE the previous pivot's rank-1 update plus that pivot's (column, scaled row):
 //     a'[r,c] = a[r,c] - col[r] * prow[c]        (r != p)         a'[p,c] = prow[c]
-// -- the same rounded product and rounded difference k_update writes, so the bits agree.  Hence
-//     k_look(k -> k+1)  decides iteration k+1 from the tableau S_{k-1} and pivot k's (col, prow)
-//     k_update(k)       streams S_{k-1} -> S_k (out of place, ping-pong buffers)
-// have the same inputs and run CONCURRENTLY on two streams; the latency-bound chain (and, when
-// sharded, the exchange of candidate rows) hides behind the HBM-bound update.  Per-iteration
-// decisions live in a 2-slot ring (slot = k & 1): IterState, colbuf, candidate row, gathered.
+// -- the same rounded product and rounded difference the update writes, so the bits agree.  Hence
+//     look(k -> k+1)  decides iteration k+1 from the tableau S_{k-1} and pivot k's (col, prow)
+//     update(k)       streams S_{k-1} -> S_k (out of place, ping-pong buffers)
+// have the same inputs and run CONCURRENTLY: the latency-bound chain -- and, when the tableau is
+// row-block sharded, the exchange of candidate pivot rows between GPUs -- hides behind the
+// HBM-bound update.  Two packagings of the same two device functions:
+//   k_iter            ONE persistent kernel per iteration: the first few CTAs play the look role,
+//                     the rest pull update tiles from a counter.  Sharded, the look role exchanges
+//                     candidates itself through peer-mapped buffers over NVLink (header from
+//                     every rank, then the winner's scaled row to every rank) -- no NCCL call,
+//                     no second stream, nothing on the host between iterations.
+//   k_look + k_update the same roles as two kernels on two streams with an NCCL all-gather in
+//                     between (used when peer mapping is unavailable).
+// Per-iteration decisions live in a 4-slot ring (slot = k & 3): IterState, pivot column,
+// candidate headers/row.
 // ==========================================================================================
 constexpr int ST_START = 101;            // ring slot holds no pending pivot (first look of a call)
-constexpr int kLookThreads = 1024;
+constexpr int ST_PEER_TIMEOUT = -7;      // == B200LP_ERR_PEER_TIMEOUT
+constexpr int kRing = 4;
+constexpr int kLookThreads = 256;        // == kPivotThreads: both roles share k_iter's CTA shape
+constexpr int kLookMaxCtas = 32;
+constexpr int kMaxWorld = 8;
 
 struct alignas(16) IterState {
-    int status;               // ST_RUNNING: pivot (j, winner of the candidates) is pending
+    int status;               // ST_RUNNING: pivot (j, p) is pending
     int j;                    // entering column
-    int p;                    // leaving row (global); unsharded only, sharded: resolve_winner()
-    int pad;
+    int p;                    // leaving row (global), -1 = this shard's candidate only (NCCL path)
+    int w;                    // rank whose scaled row is the pivot row
     long long iters;          // pivots completed before this iteration
+    long long pad;
 };
 
 struct alignas(16) Report {   // what the host polls
@@ -372,18 +386,49 @@ struct alignas(16) Report {   // what the host polls
     long long iters;
 };
 
-// Pick the global leaving row from the candidate headers (one per rank; stride in doubles).
+// Scratch of one look grid: arrival counters of its grid-wide barriers (re-armed by the last CTA
+// to leave), the per-CTA partial results of the two argmin stages, the update-tile counters.
+struct alignas(16) LookSync {
+    unsigned int bar[4];
+    unsigned int fail;
+    unsigned int tile_ctr[2];
+    unsigned int pad;
+    Cand part_enter[kLookMaxCtas];
+    Cand part_ratio[kLookMaxCtas];
+};
+
+// Peer-mapped exchange buffer, one per rank, identical layout everywhere (8-byte words):
+//   hdr  [kRing][kMaxWorld] CandHdr   candidate header of every rank
+//   row  [kRing][ld]        double    the winner's scaled pivot row
+//   flag1[kRing][kMaxWorld] u64       "header of rank r for this slot has landed" (sequence no.)
+//   flag2[kRing]            u64       "row for this slot has landed"
+struct Xchg {
+    double *peer[kMaxWorld];  // base of every rank's buffer as mapped into THIS process
+    int rank;
+    int world;
+    int64_t ld;
+    unsigned long long epoch; // high bits of the sequence numbers of this b200lp_iterate call
+};
+__host__ __device__ __forceinline__ int64_t xchg_hdr_off(int slot, int r) { return (slot * kMaxWorld + r) * kCandHdr; }
+__host__ __device__ __forceinline__ int64_t xchg_row_off(int slot, int64_t ld) { return kRing * kMaxWorld * kCandHdr + slot * ld; }
+__host__ __device__ __forceinline__ int64_t xchg_flag1_off(int slot, int r, int64_t ld) { return kRing * kMaxWorld * kCandHdr + kRing * ld + slot * kMaxWorld + r; }
+__host__ __device__ __forceinline__ int64_t xchg_flag2_off(int slot, int64_t ld) { return kRing * kMaxWorld * kCandHdr + kRing * ld + kRing * kMaxWorld + slot; }
+__host__ __device__ __forceinline__ int64_t xchg_words(int64_t ld) { return kRing * kMaxWorld * kCandHdr + kRing * ld + kRing * kMaxWorld + kRing + 4; }
+
+// Pick the global leaving row from candidate headers (hdr_stride doubles apart).
 // Same (ratio, key) lexicographic minimum on every rank == the unsharded first-index scan.
-__device__ __forceinline__ Cand resolve_winner(const double *cand_base, int64_t stride, int world,
+__device__ __forceinline__ Cand resolve_winner(const double *hdr_base, int64_t hdr_stride, int world,
                                                int *winner)
 {
     Cand best;
     best.q = 0.0; best.key = 0; best.row = -1;
     int w = 0;
     for (int g = 0; g < world; ++g) {
-        const CandHdr *h = reinterpret_cast<const CandHdr *>(cand_base + g * stride);
+        const double *h = hdr_base + g * hdr_stride;
         Cand c;
-        c.q = h->q; c.key = (int)h->key; c.row = (int)h->row;
+        c.q = __ldcg(h);
+        c.key = (int)__ldcg(reinterpret_cast<const long long *>(h) + 1);
+        c.row = (int)__ldcg(reinterpret_cast<const long long *>(h) + 2);
         const Cand nb = cand_min(best, c);
         if (nb.row != best.row) { best = nb; w = g; }
     }
@@ -394,36 +439,102 @@ __device__ __forceinline__ Cand resolve_winner(const double *cand_base, int64_t 
 struct LookArgs {
     const double *src;        // tableau S_{k-1}: this shard's block, R_local x ld
     int64_t ld;
-    int C, m_local, R_local, row0, world;
+    int C, m_local, R_local, row0, world, rank;
     int is_max, rule;
+    int slot_in, slot_out;    // ring slots of iteration k (pending) and k+1 (decided here)
     double thr_enter, thr_pivot;
     long long max_iters;      // 0 = unlimited
-    const IterState *st_in;   // ring slot of pending iteration k
-    IterState *st_out;        // ring slot of iteration k+1
-    const double *col_in;     // pivot column of iteration k (R_local)
-    double *col_out;          // pivot column of iteration k+1
-    const double *cand_in;    // candidates of iteration k: world x (hdr + ld) (own only if world == 1)
-    int64_t cand_stride;
-    double *cand_out;         // this shard's candidate for iteration k+1: hdr + ld
+    IterState *ring;          // kRing slots
+    double *colring;          // kRing x col_stride: pivot columns
+    int64_t col_stride;
+    // candidates: exchange mode 0 (one shard) / 1 (NCCL all-gather after the kernel):
+    double *candring;         // kRing x cand_stride: this shard's (hdr + scaled row)
+    const double *gathring;   // mode 1: kRing x world x cand_stride, filled by the all-gather
+    int64_t cand_stride;      // kCandHdr + ld
+    // exchange mode 2 (peer-mapped, in-kernel): xchg.peer[] != nullptr
+    Xchg xchg;
+    int mode;
     int32_t *basis;
     Report *report;
     int2 *trace;
     int trace_cap;
+    LookSync *sync;
+    unsigned long long timeout_ns;
 };
 
-// k_look: find-entering-column + find-pivoting-row + the division half of n-pivot-row
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Grid-wide barrier of the G look CTAs (co-resident by construction: the lowest block indices
+// of k_iter, or a small grid on a high-priority stream).  Data written before it is visible
+// after it to loads that bypass L1.
+__device__ __forceinline__ void look_barrier(unsigned int *ctr, int G)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        while (*reinterpret_cast<volatile unsigned int *>(ctr) < (unsigned)G) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// Every CTA reduces the same per-CTA partials in the same order: identical result everywhere.
+__device__ __forceinline__ Cand look_reduce_partials(const Cand *part, int G, Cand *s_out)
+{
+    if (threadIdx.x < 32) {
+        Cand d;
+        d.q = 0.0; d.key = 0; d.row = -1;
+        if ((int)threadIdx.x < G) {
+            const Cand *p = part + threadIdx.x;
+            d.q = __ldcg(&p->q); d.key = __ldcg(&p->key); d.row = __ldcg(&p->row);
+        }
+        d = cand_warp_min(d);
+        if (threadIdx.x == 0) *s_out = d;
+    }
+    __syncthreads();
+    return *s_out;
+}
+
+// Spin until *flag == want (a peer's system-scope store); false on timeout.
+__device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsigned long long want,
+                                          unsigned long long timeout_ns)
+{
+    const volatile unsigned long long *f = flag;
+    if (*f == want) return true;
+    const unsigned long long t0 = global_timer_ns();
+    for (;;) {
+        for (int k = 0; k < 64; ++k)
+            if (*f == want) return true;
+        if (global_timer_ns() - t0 > timeout_ns) return false;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// look role: find-entering-column + find-pivoting-row + the division half of n-pivot-row
 // (src/simplex.lisp:362-389, 344-348) for iteration k+1, evaluated on the not-yet-updated
-// tableau.  It also retires iteration k: basis[p] <- j (:358), pivot trace, iteration count,
-// and (sharded) the UNBOUNDED verdict that is only known after the exchange.  One CTA.
-__global__ void __launch_bounds__(kLookThreads) k_look(const LookArgs A)
+// tableau.  It also retires iteration k: basis[p] <- j (:358), pivot trace, iteration count.
+// G CTAs x 256 threads split each scan; three grid barriers.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void look_role(const LookArgs &A, const int cta, const int G)
 {
     __shared__ Cand red[kLookThreads / 32];
-    __shared__ Cand s_win;
-    __shared__ int s_w;
-    const IterState st = *A.st_in;
+    __shared__ Cand s_part;
+    __shared__ int s_p, s_w, s_ok;
+    __shared__ bool s_last;
     const int tid = threadIdx.x;
+    const IterState st = A.ring[A.slot_in];
+    IterState *st_out = A.ring + A.slot_out;
+    if (cta == 0 && tid == 0) {                                // re-arm next iteration's tile counter
+        A.sync->tile_ctr[A.slot_out & 1] = 0;
+    }
     if (st.status != ST_RUNNING && st.status != ST_START) {   // solve already over: pass it on
-        if (tid == 0) *A.st_out = st;
+        if (cta == 0 && tid == 0) *st_out = st;
         return;
     }
     const bool pending = st.status == ST_RUNNING;
@@ -431,203 +542,373 @@ __global__ void __launch_bounds__(kLookThreads) k_look(const LookArgs A)
     int p_local = -1;
     const double *prow = nullptr;
     if (pending) {
-        if (tid == 0) {
-            int w = 0;
-            Cand win;
-            if (A.world == 1) {
-                win.q = 0.0; win.key = 0; win.row = st.p;
-            } else {
-                win = resolve_winner(A.cand_in, A.cand_stride, A.world, &w);
-            }
-            s_win = win;
-            s_w = w;
-        }
-        __syncthreads();
-        const int p = s_win.row;
-        if (p < 0) {                                           // no rank had an eligible row
+        int p = st.p, w = st.w;
+        if (A.mode == 1) {                                     // verdict of the all-gather
             if (tid == 0) {
-                IterState o = st;
-                o.status = ST_UNBOUNDED;
-                *A.st_out = o;
-                A.report->iters = iters;
-                A.report->status = ST_UNBOUNDED;
+                int ww = 0;
+                s_p = resolve_winner(A.gathring + (int64_t)A.slot_in * A.world * A.cand_stride,
+                                     A.cand_stride, A.world, &ww).row;
+                s_w = ww;
             }
-            return;
+            __syncthreads();
+            p = s_p; w = s_w;
+            if (p < 0) {                                       // no rank had an eligible row
+                if (cta == 0 && tid == 0) {
+                    IterState o = st;
+                    o.status = ST_UNBOUNDED;
+                    *st_out = o;
+                    A.report->iters = iters;
+                    A.report->status = ST_UNBOUNDED;
+                }
+                return;
+            }
+            prow = A.gathring + ((int64_t)A.slot_in * A.world + w) * A.cand_stride + kCandHdr;
+        } else if (A.mode == 2) {
+            prow = A.xchg.peer[A.rank] + xchg_row_off(A.slot_in, A.ld);
+        } else {
+            prow = A.candring + (int64_t)A.slot_in * A.cand_stride + kCandHdr;
         }
-        prow = A.cand_in + (int64_t)s_w * A.cand_stride + kCandHdr;
         const int rel = p - A.row0;
         if (rel >= 0 && rel < A.m_local) p_local = rel;
-        if (tid == 0) {
+        if (cta == 0 && tid == 0) {
             if (p_local >= 0) A.basis[p_local] = st.j;         // (setf (aref basis p) j) :358
             if (A.trace && iters < A.trace_cap) A.trace[iters] = make_int2(st.j, p);
         }
         iters += 1;
-        __syncthreads();                                       // basis[] visible to the Bland keys
     }
-    const double *col = A.col_in;
+    const double *col = A.colring + (int64_t)A.slot_in * A.col_stride;
+    double *col_out = A.colring + (int64_t)A.slot_out * A.col_stride;
+    double *cand_out = A.candring + (int64_t)A.slot_out * A.cand_stride;
     const int nv = A.C - 1;
-
-    // ---- stage 1: entering column over the (updated) objective row ---------------------------
-    const double *obj = A.src + (int64_t)A.m_local * A.ld;
-    const double t_obj = pending ? col[A.m_local] : 0.0;
-    Cand best;
-    best.q = 0.0; best.key = 0; best.row = -1;
-    if (A.rule == 0) {
-        for (int c = tid; c < nv; c += kLookThreads) {
-            double v = obj[c];
-            if (pending) v = __dsub_rn(v, __dmul_rn(t_obj, prow[c]));
-            const double k = A.is_max ? v : -v;
-            if (best.row < 0 || k < best.q) { best.q = k; best.key = c; best.row = c; }
-        }
-    } else {
-        for (int c = tid; c < nv; c += kLookThreads) {
-            double v = obj[c];
-            if (pending) v = __dsub_rn(v, __dmul_rn(t_obj, prow[c]));
-            const double k = A.is_max ? v : -v;
-            if (k < 0.0 - A.thr_enter) { best.q = 0.0; best.key = c; best.row = c; break; }
-        }
-    }
-    best = cand_block_min<kLookThreads>(best, red);
-    {
-        const bool accept = (best.row >= 0) && (A.rule != 0 || best.q < 0.0 - A.thr_enter);
-        int fin = ST_RUNNING;
-        if (!accept) fin = ST_OPTIMAL;
-        else if (A.max_iters > 0 && iters >= A.max_iters) fin = ST_ITERATION_LIMIT;
-        if (fin != ST_RUNNING) {
-            if (tid == 0) {
-                IterState o;
-                o.status = fin; o.j = accept ? best.row : -1; o.p = -1; o.pad = 0; o.iters = iters;
-                *A.st_out = o;
-                A.report->iters = iters;
-                A.report->status = fin;
-            }
-            return;
-        }
-    }
-    const int j = best.row;
-
-    // ---- stage 2: pivot-column snapshot + ratio test over this shard's rows --------------------
-    const int rhs = A.C - 1;
-    const double pj = pending ? prow[j] : 0.0;
-    const double pb = pending ? prow[rhs] : 0.0;
+    int fin = ST_RUNNING;
+    int j = -1, win_rank = 0;
     Cand c;
     c.q = 0.0; c.key = 0; c.row = -1;
-    for (int i = tid; i < A.R_local; i += kLookThreads) {
-        const double *rowp = A.src + (int64_t)i * A.ld;
-        double a = rowp[j];
-        double t = 0.0;
-        if (pending) {
-            t = col[i];
-            a = (i == p_local) ? pj : __dsub_rn(a, __dmul_rn(t, pj));
-        }
-        A.col_out[i] = a;
-        if (i < A.m_local && 0.0 + A.thr_pivot < a) {
-            double b = rowp[rhs];
-            if (pending) b = (i == p_local) ? pb : __dsub_rn(b, __dmul_rn(t, pb));
-            Cand d;
-            d.q = __ddiv_rn(b, a);
-            d.key = A.rule ? A.basis[i] : A.row0 + i;
-            d.row = A.row0 + i;
-            c = cand_min(c, d);
-        }
-    }
-    __syncthreads();                                           // red[] reuse
-    c = cand_block_min<kLookThreads>(c, red);
 
-    // ---- stage 3: this shard's candidate row / its pivot element -------------------------------
-    CandHdr *hdr = reinterpret_cast<CandHdr *>(A.cand_out);
-    if (c.row >= 0) {
-        const int i = c.row - A.row0;
-        const double s = A.col_out[i];                         // written above, synced by the reduce
-        const double t = pending ? col[i] : 0.0;
-        const bool is_p = (i == p_local);
-        const double *rowp = A.src + (int64_t)i * A.ld;
-        double *out = A.cand_out + kCandHdr;
-        for (int cc = tid; cc < (int)A.ld; cc += kLookThreads) {
-            double v = 0.0;
-            if (cc < A.C) {
-                v = rowp[cc];
-                if (pending) v = is_p ? prow[cc] : __dsub_rn(v, __dmul_rn(t, prow[cc]));
-                v = __ddiv_rn(v, s);
+    // ---- stage 1: entering column over the (updated) objective row ---------------------------
+    {
+        const double *obj = A.src + (int64_t)A.m_local * A.ld;
+        const double t_obj = pending ? col[A.m_local] : 0.0;
+        const int chunk = (nv + G - 1) / G;
+        const int c_end = min(nv, (cta + 1) * chunk);
+        Cand best;
+        best.q = 0.0; best.key = 0; best.row = -1;
+#pragma unroll 4
+        for (int cc = cta * chunk + tid; cc < c_end; cc += kLookThreads) {
+            double v = obj[cc];
+            if (pending) v = __dsub_rn(v, __dmul_rn(t_obj, prow[cc]));
+            const double k = A.is_max ? v : -v;
+            if (A.rule == 0) {
+                if (best.row < 0 || k < best.q) { best.q = k; best.key = cc; best.row = cc; }
+            } else if (best.row < 0 && k < 0.0 - A.thr_enter) {
+                best.q = 0.0; best.key = cc; best.row = cc;   // Bland: lowest passing index
             }
-            out[cc] = v;
+        }
+        best = cand_block_min<kLookThreads>(best, red);
+        if (G > 1) {
+            if (tid == 0) A.sync->part_enter[cta] = best;
+            look_barrier(&A.sync->bar[0], G);
+            best = look_reduce_partials(A.sync->part_enter, G, &s_part);
+        }
+        const bool accept = (best.row >= 0) && (A.rule != 0 || best.q < 0.0 - A.thr_enter);
+        if (!accept) fin = ST_OPTIMAL;
+        else if (A.max_iters > 0 && iters >= A.max_iters) fin = ST_ITERATION_LIMIT;
+        j = accept ? best.row : -1;
+    }
+
+    if (fin == ST_RUNNING) {
+        // ---- stage 2: pivot-column snapshot + ratio test over this shard's rows ----------------
+        const int rhs = A.C - 1;
+        const double pj = pending ? prow[j] : 0.0;
+        const double pb = pending ? prow[rhs] : 0.0;
+        const int chunk = (A.R_local + G - 1) / G;
+        const int r_end = min(A.R_local, (cta + 1) * chunk);
+#pragma unroll 2
+        for (int i = cta * chunk + tid; i < r_end; i += kLookThreads) {
+            const double *rowp = A.src + (int64_t)i * A.ld;
+            double a = rowp[j];
+            double b = rowp[rhs];
+            if (pending) {
+                const double t = col[i];
+                a = (i == p_local) ? pj : __dsub_rn(a, __dmul_rn(t, pj));
+                b = (i == p_local) ? pb : __dsub_rn(b, __dmul_rn(t, pb));
+            }
+            col_out[i] = a;
+            if (i < A.m_local && 0.0 + A.thr_pivot < a) {
+                Cand d;
+                d.q = __ddiv_rn(b, a);
+                d.key = A.rule ? ((i == p_local) ? st.j : A.basis[i]) : A.row0 + i;
+                d.row = A.row0 + i;
+                c = cand_min(c, d);
+            }
+        }
+        __syncthreads();                                       // red[] reuse
+        c = cand_block_min<kLookThreads>(c, red);
+        if (G > 1) {
+            if (tid == 0) A.sync->part_ratio[cta] = c;
+            look_barrier(&A.sync->bar[1], G);
+            c = look_reduce_partials(A.sync->part_ratio, G, &s_part);
+        }
+        // c = this shard's best (ratio, key, row)
+
+        bool i_win = true;                                     // modes 0/1: always scale own row
+        if (A.mode == 2) {
+            // ---- header exchange over NVLink: every rank -> every rank -------------------------
+            const unsigned long long seq = A.xchg.epoch + (unsigned long long)iters + 1ull;
+            if (cta == 0 && tid < A.world) {
+                double *h = A.xchg.peer[tid] + xchg_hdr_off(A.slot_out, A.rank);
+                h[0] = c.q;
+                reinterpret_cast<long long *>(h)[1] = c.key;
+                reinterpret_cast<long long *>(h)[2] = c.row;
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned long long *>(
+                    A.xchg.peer[tid] + xchg_flag1_off(A.slot_out, A.rank, A.ld)) = seq;
+            }
+            if (tid == 0) s_ok = 1;
+            __syncthreads();
+            if (tid < A.world) {
+                const unsigned long long *f = reinterpret_cast<const unsigned long long *>(
+                    A.xchg.peer[A.rank] + xchg_flag1_off(A.slot_out, tid, A.ld));
+                if (!wait_flag(f, seq, A.timeout_ns)) s_ok = 0;
+            }
+            __syncthreads();
+            if (!s_ok) {
+                fin = ST_PEER_TIMEOUT;
+            } else {
+                if (tid == 0) {
+                    __threadfence_system();
+                    int ww = 0;
+                    s_p = resolve_winner(A.xchg.peer[A.rank] + xchg_hdr_off(A.slot_out, 0), kCandHdr,
+                                         A.world, &ww).row;
+                    s_w = ww;
+                }
+                __syncthreads();
+                win_rank = s_w;
+                i_win = (win_rank == A.rank) && s_p >= 0;
+                // from here on c.row is the GLOBAL leaving row (or -1: unbounded)
+                if (!i_win) { c.row = s_p; }
+            }
+        }
+
+        // ---- stage 3: candidate row / its pivot element -----------------------------------------
+        if (fin == ST_RUNNING && i_win && c.row >= 0) {
+            const int i = c.row - A.row0;
+            const double s = __ldcg(col_out + i);              // written by another CTA in stage 2
+            const double t = pending ? col[i] : 0.0;
+            const bool is_p = (i == p_local);
+            const double *rowp = A.src + (int64_t)i * A.ld;
+            const int ld = (int)A.ld;
+            const int chunk3 = (ld + G - 1) / G;
+            const int e3 = min(ld, (cta + 1) * chunk3);
+#pragma unroll 4
+            for (int cc = cta * chunk3 + tid; cc < e3; cc += kLookThreads) {
+                double v = 0.0;
+                if (cc < A.C) {
+                    v = rowp[cc];
+                    if (pending) v = is_p ? prow[cc] : __dsub_rn(v, __dmul_rn(t, prow[cc]));
+                    v = __ddiv_rn(v, s);
+                }
+                if (A.mode == 2) {
+                    const int64_t off = xchg_row_off(A.slot_out, A.ld) + cc;
+                    for (int g = 0; g < A.world; ++g) A.xchg.peer[g][off] = v;
+                } else {
+                    cand_out[kCandHdr + cc] = v;
+                }
+            }
+            if (A.mode == 2) __threadfence_system();
         }
     }
+
+    // ---- leave: the last CTA publishes the verdict and re-arms the barriers --------------------
+    __syncthreads();
     if (tid == 0) {
-        hdr->q = c.q; hdr->key = c.key; hdr->row = c.row; hdr->pad = 0;
-        IterState o;
-        o.status = ST_RUNNING; o.j = j; o.p = c.row; o.pad = 0; o.iters = iters;
-        if (A.world == 1 && c.row < 0) {
-            o.status = ST_UNBOUNDED;
-            A.report->iters = iters;
-            A.report->status = ST_UNBOUNDED;
-        }
-        *A.st_out = o;
+        __threadfence();
+        if (fin == ST_PEER_TIMEOUT) atomicOr(&A.sync->fail, 1u);
+        s_last = atomicAdd(&A.sync->bar[2], 1u) == (unsigned)(G - 1);
     }
+    __syncthreads();
+    if (!s_last) return;
+    if (tid == 0) {
+        __threadfence();
+        if (A.sync->fail) fin = ST_PEER_TIMEOUT;
+        A.sync->bar[0] = 0; A.sync->bar[1] = 0; A.sync->bar[2] = 0; A.sync->fail = 0;
+        s_ok = 1;
+    }
+    __syncthreads();
+    if (A.mode == 2 && fin == ST_RUNNING && c.row >= 0) {
+        // the winner's row is complete on every rank (all its CTAs fenced before arriving):
+        // raise flag2 everywhere, then wait for ours so that the kernel ends with the row present
+        const unsigned long long seq = A.xchg.epoch + (unsigned long long)iters + 1ull;
+        if (win_rank == A.rank && tid < A.world) {
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long *>(
+                A.xchg.peer[tid] + xchg_flag2_off(A.slot_out, A.ld)) = seq;
+        }
+        if (tid == 0) {
+            const unsigned long long *f = reinterpret_cast<const unsigned long long *>(
+                A.xchg.peer[A.rank] + xchg_flag2_off(A.slot_out, A.ld));
+            if (!wait_flag(f, seq, A.timeout_ns)) s_ok = 0;
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (!s_ok) fin = ST_PEER_TIMEOUT;
+    }
+    if (tid != 0) return;
+    IterState o;
+    o.status = fin; o.j = j; o.p = -1; o.w = win_rank; o.iters = iters; o.pad = 0;
+    if (fin == ST_RUNNING) {
+        if (A.mode != 2) {
+            CandHdr *hdr = reinterpret_cast<CandHdr *>(cand_out);
+            hdr->q = c.q; hdr->key = c.key; hdr->row = c.row; hdr->pad = 0;
+        }
+        o.p = c.row;
+        if (A.mode != 1 && c.row < 0) o.status = ST_UNBOUNDED;
+    }
+    if (o.status != ST_RUNNING) {
+        A.report->iters = iters;
+        A.report->status = o.status;
+    }
+    *st_out = o;
 }
 
-// k_update: the rank-1 update of iteration k, streaming src -> dst (dst may equal src).
-// Same tiling as k_pivot; reads its decisions from the ring slot and never writes state.
-template <int TR, int UNROLL, int VEC, bool STREAM>
-__global__ void __launch_bounds__(kPivotThreads)
-k_update(const double *src, double *dst, int64_t ld, int m_local, int R_local, int row0, int world,
-         const IterState *__restrict__ st, const double *__restrict__ colbuf,
-         const double *__restrict__ cand_base, int64_t cand_stride)
+// ------------------------------------------------------------------------------------------
+// update role: n-pivot-row part 2 (src/simplex.lisp:349-358) for one tile of TR rows x 256
+// double2 columns, streaming src -> dst.  16*R*C algorithmic bytes per iteration in total.
+// ------------------------------------------------------------------------------------------
+struct UpdateArgs {
+    const double *src;
+    double *dst;
+    int64_t ld;
+    int m_local, R_local, row0, world, mode, slot;
+    const IterState *ring;
+    const double *colring;
+    int64_t col_stride;
+    const double *candring;   // mode 0
+    const double *gathring;   // mode 1
+    int64_t cand_stride;
+    const double *xrow;       // mode 2: this rank's xchg row ring base (slot 0)
+    unsigned int *tile_ctr;   // k_iter only
+};
+
+// Which row is the pivot row and where its scaled copy lives; false = nothing to apply.
+__device__ __forceinline__ bool update_decision(const UpdateArgs &U, int *p_local, const double **prow)
 {
-    if (st->status != ST_RUNNING) return;
-    __shared__ double s_col[TR];
-    __shared__ int s_p, s_w;
-    if (threadIdx.x == 0) {
-        int w = 0, p = st->p;
-        if (world > 1) p = resolve_winner(cand_base, cand_stride, world, &w).row;
-        s_p = p; s_w = w;
+    const IterState *st = U.ring + U.slot;
+    if (st->status != ST_RUNNING) return false;
+    int p = st->p, w = st->w;
+    const double *row;
+    if (U.mode == 1) {
+        const double *base = U.gathring + (int64_t)U.slot * U.world * U.cand_stride;
+        p = resolve_winner(base, U.cand_stride, U.world, &w).row;
+        row = base + (int64_t)w * U.cand_stride + kCandHdr;
+    } else if (U.mode == 2) {
+        row = U.xrow + (int64_t)U.slot * U.ld;
+    } else {
+        row = U.candring + (int64_t)U.slot * U.cand_stride + kCandHdr;
     }
-    const int ldv = (int)(ld >> 1);
-    const int r_begin = blockIdx.y * TR;
-    const int r_end = min(R_local, r_begin + TR);
-    for (int t = threadIdx.x; t < TR; t += kPivotThreads)
-        s_col[t] = (r_begin + t < r_end) ? colbuf[r_begin + t] : 0.0;
-    __syncthreads();
-    if (s_p < 0) return;                                       // unbounded: nothing to apply
-    const int p_rel = s_p - row0;
-    const int p_local = (p_rel >= 0 && p_rel < m_local) ? p_rel : -1;
-    const double2 *prow2 =
-        reinterpret_cast<const double2 *>(cand_base + (int64_t)s_w * cand_stride + kCandHdr);
-    int cv[VEC];
-    double2 pr[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-        cv[v] = (blockIdx.x * VEC + v) * kPivotThreads + threadIdx.x;
-        pr[v] = (cv[v] < ldv) ? prow2[cv[v]] : make_double2(0.0, 0.0);
-    }
-    const double2 *src2 = reinterpret_cast<const double2 *>(src);
-    double2 *dst2 = reinterpret_cast<double2 *>(dst);
+    if (p < 0) return false;
+    const int rel = p - U.row0;
+    *p_local = (rel >= 0 && rel < U.m_local) ? rel : -1;
+    *prow = row;
+    return true;
+}
+
+template <int TR, int UNROLL, bool STREAM>
+__device__ __forceinline__ void update_tile(const double2 *src2, double2 *dst2, const int ldv,
+                                            const int cv, const double2 pr, const int r_begin,
+                                            const int r_end, const int p_local, const double *s_col)
+{
+    if (cv >= ldv) return;
     for (int r = r_begin; r < r_end; r += UNROLL) {
-        double2 a[UNROLL][VEC];
+        double2 a[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
-#pragma unroll
-            for (int v = 0; v < VEC; ++v)
-                if (r + u < r_end && cv[v] < ldv)
-                    a[u][v] = ld_tab<STREAM>(src2 + (int64_t)(r + u) * ldv + cv[v]);
+            if (r + u < r_end) a[u] = ld_tab<STREAM>(src2 + (int64_t)(r + u) * ldv + cv);
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             if (r + u < r_end) {
                 const double t = s_col[r + u - r_begin];
-                const bool is_p = (r + u == p_local);
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) {
-                    if (cv[v] < ldv) {
-                        double2 o;
-                        o.x = __dsub_rn(a[u][v].x, __dmul_rn(t, pr[v].x));
-                        o.y = __dsub_rn(a[u][v].y, __dmul_rn(t, pr[v].y));
-                        if (is_p) o = pr[v];
-                        st_tab<STREAM>(dst2 + (int64_t)(r + u) * ldv + cv[v], o);
-                    }
-                }
+                double2 o;
+                o.x = __dsub_rn(a[u].x, __dmul_rn(t, pr.x));
+                o.y = __dsub_rn(a[u].y, __dmul_rn(t, pr.y));
+                if (r + u == p_local) o = pr;
+                st_tab<STREAM>(dst2 + (int64_t)(r + u) * ldv + cv, o);
             }
         }
     }
+}
+
+// Two-kernel packaging, update half: static 2-D grid (x: column tiles, y: row blocks).
+template <int TR, int UNROLL, bool STREAM>
+__global__ void __launch_bounds__(kPivotThreads) k_update(const UpdateArgs U)
+{
+    __shared__ double s_col[TR];
+    __shared__ int s_pl, s_go;
+    __shared__ const double *s_row;
+    if (threadIdx.x == 0) {
+        int pl = -1;
+        const double *row = nullptr;
+        s_go = update_decision(U, &pl, &row) ? 1 : 0;
+        s_pl = pl; s_row = row;
+    }
+    __syncthreads();
+    if (!s_go) return;
+    const int ldv = (int)(U.ld >> 1);
+    const int r_begin = blockIdx.y * TR;
+    const int r_end = min(U.R_local, r_begin + TR);
+    const double *col = U.colring + (int64_t)U.slot * U.col_stride;
+    for (int t = threadIdx.x; t < TR; t += kPivotThreads)
+        s_col[t] = (r_begin + t < r_end) ? col[r_begin + t] : 0.0;
+    const int cv = blockIdx.x * kPivotThreads + threadIdx.x;
+    const double2 pr = (cv < ldv) ? reinterpret_cast<const double2 *>(s_row)[cv] : make_double2(0.0, 0.0);
+    __syncthreads();
+    update_tile<TR, UNROLL, STREAM>(reinterpret_cast<const double2 *>(U.src),
+                                    reinterpret_cast<double2 *>(U.dst), ldv, cv, pr, r_begin, r_end,
+                                    s_pl, s_col);
+}
+
+// Two-kernel packaging, look half.
+__global__ void __launch_bounds__(kLookThreads) k_look(const LookArgs A)
+{
+    look_role(A, blockIdx.x, gridDim.x);
+}
+
+// One-kernel packaging: CTAs [0, look_ctas) look ahead (and exchange); CTA look_ctas + t streams
+// tile t (row-block major, so consecutive CTAs cover one 64-row slab left to right).  The block
+// scheduler dispatches in index order, so the look CTAs are resident before any tile.
+template <int TR, int UNROLL, bool STREAM>
+__global__ void __launch_bounds__(kPivotThreads, UNROLL >= 16 ? 2 : 4)
+k_iter(const LookArgs A, const UpdateArgs U, const int look_ctas)
+{
+    if ((int)blockIdx.x < look_ctas) {
+        look_role(A, blockIdx.x, look_ctas);
+        return;
+    }
+    __shared__ double s_col[TR];
+    __shared__ int s_pl, s_go;
+    __shared__ const double *s_row;
+    if (threadIdx.x == 0) {
+        int pl = -1;
+        const double *row = nullptr;
+        s_go = update_decision(U, &pl, &row) ? 1 : 0;
+        s_pl = pl; s_row = row;
+    }
+    const int ldv = (int)(U.ld >> 1);
+    const int tiles_x = (ldv + kPivotThreads - 1) / kPivotThreads;
+    const int tile = (int)blockIdx.x - look_ctas;
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int r_begin = ty * TR;
+    const int r_end = min(U.R_local, r_begin + TR);
+    const double *col = U.colring + (int64_t)U.slot * U.col_stride;
+    for (int t = threadIdx.x; t < TR; t += kPivotThreads)
+        s_col[t] = (r_begin + t < r_end) ? col[r_begin + t] : 0.0;
+    __syncthreads();
+    if (!s_go) return;
+    const int cv = tx * kPivotThreads + threadIdx.x;
+    const double2 pr = (cv < ldv) ? reinterpret_cast<const double2 *>(s_row)[cv] : make_double2(0.0, 0.0);
+    update_tile<TR, UNROLL, STREAM>(reinterpret_cast<const double2 *>(U.src),
+                                    reinterpret_cast<double2 *>(U.dst), ldv, cv, pr, r_begin, r_end,
+                                    s_pl, s_col);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -86,19 +86,25 @@ struct Shard {
     int cur = 0;                // which buffer holds the current tableau
     double *tab = nullptr;      // == tabs[cur]
     int32_t *basis = nullptr;
-    // 2-slot decision ring of the pipelined loop (slot = iteration & 1); the step-by-step API
-    // uses slot 0 through the aliases below
-    double *colring[2] = {nullptr, nullptr};
-    double *candring[2] = {nullptr, nullptr};
-    double *gathring[2] = {nullptr, nullptr};
-    IterState *ring = nullptr;  // 2 slots
+    // kRing-slot decision ring of the pipelined loop (slot = iteration & 3); the step-by-step
+    // API uses slot 0 through the aliases below
+    double *colring = nullptr;  // kRing x R_local
+    double *candring = nullptr; // kRing x (kCandHdr + ld)
+    double *gathring = nullptr; // kRing x world x (kCandHdr + ld)   (exchange mode 1 only)
+    IterState *ring = nullptr;  // kRing slots
+    LookSync *look_sync = nullptr;
+    int look_ctas = 1;
+    int iter_ctas = 0;          // grid of k_iter (look_ctas + persistent update CTAs)
+    double *xbuf = nullptr;     // peer-mapped exchange buffer (exchange mode 2), see struct Xchg
+    Xchg xchg;                  // every rank's xbuf as mapped here
+    bool ipc_opened[kMaxWorld] = {false, false, false, false, false, false, false, false};
     Report *report = nullptr;
     Report *h_report = nullptr; // pinned, 2 slots
     cudaEvent_t ev_look[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_upd[4] = {nullptr, nullptr, nullptr, nullptr};
-    double *colbuf = nullptr;   // == colring[0]
-    double *cand = nullptr;     // == candring[0]: CandHdr + ld doubles
-    double *gathered = nullptr; // == gathring[0]: world * (kCandHdr + ld) doubles (sharded only)
+    double *colbuf = nullptr;   // == colring slot 0
+    double *cand = nullptr;     // == candring slot 0: CandHdr + ld doubles
+    double *gathered = nullptr; // == gathring slot 0: world * (kCandHdr + ld) doubles
     double *colout = nullptr;   // R_local doubles, RHS gather
     DevState *st = nullptr;
     Cand *partials = nullptr;
@@ -108,6 +114,7 @@ struct Shard {
     ncclComm_t comm = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_poll[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_pivot; // pairs
+    std::vector<cudaEvent_t> ev_lookt; // triples: before look, after look, after exchange
     int ratio_blocks = 0;
 };
 
@@ -128,6 +135,12 @@ struct b200lp_solver {
     int64_t kernel_launches = 0;
     int64_t pivot_launches_timed = 0;
     size_t ev_used = 0;
+    size_t evl_used = 0;
+    // how sharded candidates travel: 0 one shard, 1 NCCL all-gather between two kernels,
+    // 2 peer-mapped buffers written by the look role inside k_iter
+    int xmode = 0;
+    unsigned long long epoch = 0;
+    unsigned long long peer_timeout_ns = 20ull * 1000 * 1000 * 1000;
 };
 
 namespace b200lp {
@@ -152,19 +165,26 @@ static int alloc_shard(b200lp_solver *s, Shard &sh)
     sh.tab = sh.tabs[0];
     CU_TRY(cudaMalloc(&sh.basis, sizeof(int32_t) * std::max(1, sh.m_local)));
     CU_TRY(cudaMalloc(&sh.colout, sizeof(double) * sh.R_local));
-    for (int k = 0; k < 2; ++k) {
-        CU_TRY(cudaMalloc(&sh.colring[k], sizeof(double) * sh.R_local));
-        CU_TRY(cudaMalloc(&sh.candring[k], sizeof(double) * stride));
-        CU_TRY(cudaMemsetAsync(sh.candring[k], 0, sizeof(double) * stride, sh.stream));
-        if (s->world > 1) {
-            CU_TRY(cudaMalloc(&sh.gathring[k], sizeof(double) * stride * s->world));
-            CU_TRY(cudaMemsetAsync(sh.gathring[k], 0, sizeof(double) * stride * s->world, sh.stream));
-        }
+    CU_TRY(cudaMalloc(&sh.colring, sizeof(double) * sh.R_local * kRing));
+    CU_TRY(cudaMalloc(&sh.candring, sizeof(double) * stride * kRing));
+    CU_TRY(cudaMemsetAsync(sh.candring, 0, sizeof(double) * stride * kRing, sh.stream));
+    if (s->world > 1) {
+        CU_TRY(cudaMalloc(&sh.gathring, sizeof(double) * stride * s->world * kRing));
+        CU_TRY(cudaMemsetAsync(sh.gathring, 0, sizeof(double) * stride * s->world * kRing, sh.stream));
+        CU_TRY(cudaMalloc(&sh.xbuf, sizeof(double) * xchg_words(sh.ld)));
+        CU_TRY(cudaMemsetAsync(sh.xbuf, 0, sizeof(double) * xchg_words(sh.ld), sh.stream));
     }
-    sh.colbuf = sh.colring[0];
-    sh.cand = sh.candring[0];
-    sh.gathered = sh.gathring[0];
-    CU_TRY(cudaMalloc(&sh.ring, 2 * sizeof(IterState)));
+    std::memset(&sh.xchg, 0, sizeof(sh.xchg));
+    sh.xchg.rank = sh.rank; sh.xchg.world = s->world; sh.xchg.ld = sh.ld;
+    sh.colbuf = sh.colring;
+    sh.cand = sh.candring;
+    sh.gathered = sh.gathring;
+    CU_TRY(cudaMalloc(&sh.ring, kRing * sizeof(IterState)));
+    CU_TRY(cudaMalloc(&sh.look_sync, sizeof(LookSync)));
+    CU_TRY(cudaMemsetAsync(sh.look_sync, 0, sizeof(LookSync), sh.stream));
+    // enough look CTAs that each thread touches only a few cells per scan; one CTA (no grid
+    // barriers) when the rows are short
+    sh.look_ctas = sh.ld <= 4096 ? 1 : (int)std::min<int64_t>(kLookMaxCtas, (sh.ld + 1023) / 1024);
     CU_TRY(cudaMalloc(&sh.report, sizeof(Report)));
     CU_TRY(cudaMallocHost(&sh.h_report, 2 * sizeof(Report)));
     for (int k = 0; k < 4; ++k) {
@@ -196,10 +216,10 @@ static void free_shard(Shard &sh)
     if (sh.look_stream) cudaStreamSynchronize(sh.look_stream);
     if (sh.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(sh.comm);
     cudaFree(sh.tabs[0]); cudaFree(sh.tabs[1]); cudaFree(sh.basis); cudaFree(sh.colout);
-    for (int k = 0; k < 2; ++k) {
-        cudaFree(sh.colring[k]); cudaFree(sh.candring[k]); cudaFree(sh.gathring[k]);
-    }
-    cudaFree(sh.ring); cudaFree(sh.report);
+    for (int g = 0; g < kMaxWorld; ++g)
+        if (sh.ipc_opened[g] && sh.xchg.peer[g]) cudaIpcCloseMemHandle(sh.xchg.peer[g]);
+    cudaFree(sh.colring); cudaFree(sh.candring); cudaFree(sh.gathring); cudaFree(sh.xbuf);
+    cudaFree(sh.ring); cudaFree(sh.report); cudaFree(sh.look_sync);
     cudaFree(sh.partials); cudaFree(sh.st);
     cudaFree(sh.trace);
     if (sh.h_report) cudaFreeHost(sh.h_report);
@@ -211,6 +231,7 @@ static void free_shard(Shard &sh)
     if (sh.h_st) cudaFreeHost(sh.h_st);
     if (sh.h_trace) cudaFreeHost(sh.h_trace);
     for (cudaEvent_t e : sh.ev_pivot) cudaEventDestroy(e);
+    for (cudaEvent_t e : sh.ev_lookt) cudaEventDestroy(e);
     if (sh.ev_begin) cudaEventDestroy(sh.ev_begin);
     if (sh.ev_end) cudaEventDestroy(sh.ev_end);
     for (int k = 0; k < 2; ++k) if (sh.ev_poll[k]) cudaEventDestroy(sh.ev_poll[k]);
@@ -332,7 +353,9 @@ static int exchange(b200lp_solver *s, int slot = 0, bool on_look_stream = false)
     if (s->shards.size() > 1) NCCL_TRY(g_nccl.GroupStart());
     for (Shard &sh : s->shards) {
         if (s->shards.size() > 1) cudaSetDevice(sh.device);
-        NCCL_TRY(g_nccl.AllGather(sh.candring[slot], sh.gathring[slot], bytes, ncclChar, sh.comm,
+        const int64_t stride = kCandHdr + sh.ld;
+        NCCL_TRY(g_nccl.AllGather(sh.candring + slot * stride, sh.gathring + slot * s->world * stride,
+                                  bytes, ncclChar, sh.comm,
                                   on_look_stream ? sh.look_stream : sh.stream));
     }
     if (s->shards.size() > 1) NCCL_TRY(g_nccl.GroupEnd());
@@ -379,80 +402,174 @@ static int enqueue_iteration(b200lp_solver *s, bool do_enter, bool with_trace, b
     return B200LP_OK;
 }
 
-// ---- pipelined loop: k_look(k -> k+1) on the look stream, k_update(k) on the main stream -----
+// ---- pipelined loop ------------------------------------------------------------------------------
+// look(k -> k+1) reads the tableau before pivot k (buffer cur + (k-1), cur itself for k = 0) and
+// ring slot k; update(k) streams that buffer into the other one.
+static void fill_args(b200lp_solver *s, Shard &sh, long long k, long long cap, LookArgs *a,
+                      UpdateArgs *u)
+{
+    const int slot = (int)(k & (kRing - 1)), out = (int)((k + 1) & (kRing - 1));
+    const double *src = sh.tabs[(sh.cur + (int)((k > 0 ? k - 1 : 0) & 1)) & 1];
+    const int64_t stride = kCandHdr + sh.ld;
+    a->src = src; a->ld = sh.ld;
+    a->C = (int)s->C; a->m_local = sh.m_local; a->R_local = sh.R_local; a->row0 = (int)sh.row0;
+    a->world = s->world; a->rank = sh.rank; a->is_max = s->is_max; a->rule = s->opts.pivot_rule;
+    a->slot_in = slot; a->slot_out = out;
+    a->thr_enter = s->thr_enter; a->thr_pivot = s->thr_pivot;
+    a->max_iters = cap;
+    a->ring = sh.ring; a->colring = sh.colring; a->col_stride = sh.R_local;
+    a->candring = sh.candring; a->gathring = sh.gathring; a->cand_stride = stride;
+    a->xchg = sh.xchg; a->xchg.epoch = s->epoch;
+    a->mode = s->xmode;
+    a->basis = sh.basis; a->report = sh.report;
+    a->trace = sh.trace; a->trace_cap = s->opts.trace_capacity;
+    a->sync = sh.look_sync;
+    a->timeout_ns = s->peer_timeout_ns;
+    u->src = src;
+    u->dst = sh.tabs[(sh.cur + (int)(k & 1)) & 1];
+    u->ld = sh.ld; u->m_local = sh.m_local; u->R_local = sh.R_local; u->row0 = (int)sh.row0;
+    u->world = s->world; u->mode = s->xmode; u->slot = slot;
+    u->ring = sh.ring; u->colring = sh.colring; u->col_stride = sh.R_local;
+    u->candring = sh.candring; u->gathring = sh.gathring; u->cand_stride = stride;
+    u->xrow = sh.xbuf ? sh.xbuf + xchg_row_off(0, sh.ld) : nullptr;
+    u->tile_ctr = &sh.look_sync->tile_ctr[slot & 1];
+}
+
+static int pick_variant(const b200lp_solver *s, const Shard &sh)
+{
+    int v = s->opts.pivot_variant;
+    if (v == 0) {
+        // Two ping-pong buffers that fit the 126 MB L2 keep default caching; larger tableaus
+        // stream with the deepest load batch (16 rows in flight per thread: best on B200 at
+        // every size > L2, profiles/r01_variant_sweep_*.json).
+        const double bytes = 8.0 * (double)sh.ld * sh.R_local;
+        v = bytes > 48e6 ? 6 : 2;
+    }
+    return v;
+}
+
+// variant -> (TR, UNROLL, STREAM); 4 and 7 are kept as aliases of their one-vector forms
+#define B200LP_VARIANTS(X) \
+    switch (v) {                       \
+    default:                           \
+    case 1: X(64, 8, true); break;     \
+    case 2: X(64, 8, false); break;    \
+    case 3: X(128, 8, true); break;    \
+    case 4: X(64, 4, true); break;     \
+    case 5: X(32, 8, true); break;     \
+    case 6: X(64, 16, true); break;    \
+    case 7: X(128, 8, true); break;    \
+    case 8: X(64, 4, true); break;     \
+    case 9: X(128, 16, false); break;  \
+    }
+
+template <int TR, int UNROLL, bool STREAM>
+static cudaError_t launch_iter_t(Shard &sh, const LookArgs &a, const UpdateArgs &u)
+{
+    if (sh.iter_ctas == 0) {
+        const int64_t ldv = sh.ld / 2;
+        const int64_t ntiles = ((ldv + kPivotThreads - 1) / kPivotThreads) * ((sh.R_local + TR - 1) / TR);
+        sh.iter_ctas = sh.look_ctas + (int)ntiles;
+    }
+    k_iter<TR, UNROLL, STREAM><<<sh.iter_ctas, kPivotThreads, 0, sh.stream>>>(a, u, sh.look_ctas);
+    return cudaGetLastError();
+}
+
+static int launch_iter(b200lp_solver *s, Shard &sh, long long k, long long cap)
+{
+    LookArgs a;
+    UpdateArgs u;
+    fill_args(s, sh, k, cap, &a, &u);
+    const int v = pick_variant(s, sh);
+#define X(TR, UN, ST) CU_TRY((launch_iter_t<TR, UN, ST>(sh, a, u)))
+    B200LP_VARIANTS(X)
+#undef X
+    s->kernel_launches++;
+    return B200LP_OK;
+}
+
 static void launch_look(b200lp_solver *s, Shard &sh, long long k, long long cap)
 {
-    const int in = (int)(k & 1), out = in ^ 1;
     LookArgs a;
-    // look(k -> k+1) reads the tableau before pivot k: buffer cur + (k-1) (cur itself for k = 0)
-    a.src = sh.tabs[(sh.cur + (int)((k > 0 ? k - 1 : 0) & 1)) & 1];
-    a.ld = sh.ld;
-    a.C = (int)s->C; a.m_local = sh.m_local; a.R_local = sh.R_local; a.row0 = (int)sh.row0;
-    a.world = s->world; a.is_max = s->is_max; a.rule = s->opts.pivot_rule;
-    a.thr_enter = s->thr_enter; a.thr_pivot = s->thr_pivot;
-    a.max_iters = cap;
-    a.st_in = sh.ring + in; a.st_out = sh.ring + out;
-    a.col_in = sh.colring[in]; a.col_out = sh.colring[out];
-    a.cand_in = s->world > 1 ? sh.gathring[in] : sh.candring[in];
-    a.cand_stride = kCandHdr + sh.ld;
-    a.cand_out = sh.candring[out];
-    a.basis = sh.basis; a.report = sh.report;
-    a.trace = sh.trace; a.trace_cap = s->opts.trace_capacity;
-    k_look<<<1, kLookThreads, 0, sh.look_stream>>>(a);
+    UpdateArgs u;
+    fill_args(s, sh, k, cap, &a, &u);
+    k_look<<<sh.look_ctas, kLookThreads, 0, sh.look_stream>>>(a);
     s->kernel_launches++;
 }
 
-template <int TR, int UNROLL, int VEC, bool STREAM>
-static void launch_update_t(b200lp_solver *s, Shard &sh, long long k)
+template <int TR, int UNROLL, bool STREAM>
+static void launch_update_t(Shard &sh, const UpdateArgs &u)
 {
-    const int slot = (int)(k & 1);
-    const double *src = sh.tabs[(sh.cur + (int)((k - 1) & 1)) & 1];
-    double *dst = sh.tabs[(sh.cur + (int)(k & 1)) & 1];
     const int ldv = (int)(sh.ld / 2);
-    dim3 grid((ldv + kPivotThreads * VEC - 1) / (kPivotThreads * VEC), (sh.R_local + TR - 1) / TR);
-    k_update<TR, UNROLL, VEC, STREAM><<<grid, kPivotThreads, 0, sh.stream>>>(
-        src, dst, sh.ld, sh.m_local, sh.R_local, (int)sh.row0, s->world, sh.ring + slot,
-        sh.colring[slot], s->world > 1 ? sh.gathring[slot] : sh.candring[slot], kCandHdr + sh.ld);
+    dim3 grid((ldv + kPivotThreads - 1) / kPivotThreads, (sh.R_local + TR - 1) / TR);
+    k_update<TR, UNROLL, STREAM><<<grid, kPivotThreads, 0, sh.stream>>>(u);
 }
 
 static void launch_update(b200lp_solver *s, Shard &sh, long long k)
 {
-    int v = s->opts.pivot_variant;
-    if (v == 0) {
-        // Tableaus that fit the 126 MB L2 keep default caching; larger ones stream with the
-        // deepest load batch (16 rows in flight per thread: best on B200 at every size > L2,
-        // profiles/r01_variant_sweep_*.json).
-        const double bytes = 8.0 * (double)sh.ld * sh.R_local;
-        v = bytes > 48e6 ? 6 : 2;
-    }
-    switch (v) {
-    default:
-    case 1: launch_update_t<64, 8, 1, true>(s, sh, k); break;
-    case 2: launch_update_t<64, 8, 1, false>(s, sh, k); break;
-    case 3: launch_update_t<128, 8, 1, true>(s, sh, k); break;
-    case 4: launch_update_t<64, 4, 2, true>(s, sh, k); break;
-    case 5: launch_update_t<32, 8, 1, true>(s, sh, k); break;
-    case 6: launch_update_t<64, 16, 1, true>(s, sh, k); break;
-    case 7: launch_update_t<128, 8, 2, true>(s, sh, k); break;
-    case 8: launch_update_t<64, 4, 1, true>(s, sh, k); break;
-    case 9: launch_update_t<128, 16, 1, false>(s, sh, k); break;
-    }
+    LookArgs a;
+    UpdateArgs u;
+    fill_args(s, sh, k, 0, &a, &u);
+    const int v = pick_variant(s, sh);
+#define X(TR, UN, ST) launch_update_t<TR, UN, ST>(sh, u)
+    B200LP_VARIANTS(X)
+#undef X
     s->kernel_launches++;
 }
 
-// look(k -> k+1) (+ exchange of its candidates) on every local shard; it may start once
-// update(k-1) has produced the tableau it reads.
-static int enqueue_look(b200lp_solver *s, long long k, long long cap)
+// One fused iteration kernel on every local shard: update(k) || look(k -> k+1) (+ in-kernel exchange).
+static int enqueue_iter(b200lp_solver *s, long long k, long long cap, bool time_pivot)
 {
     const bool multi = s->shards.size() > 1;
     for (Shard &sh : s->shards) {
         if (multi) CU_TRY(cudaSetDevice(sh.device));
-        if (k > 1) CU_TRY(cudaStreamWaitEvent(sh.look_stream, sh.ev_upd[(k - 1) & 3], 0));
-        launch_look(s, sh, k, cap);
+        const bool timed = time_pivot && &sh == &s->shards[0];
+        if (timed) {
+            if (sh.ev_pivot.size() < s->ev_used + 2) {
+                cudaEvent_t a, b;
+                CU_TRY(cudaEventCreate(&a));
+                CU_TRY(cudaEventCreate(&b));
+                sh.ev_pivot.push_back(a);
+                sh.ev_pivot.push_back(b);
+            }
+            CU_TRY(cudaEventRecord(sh.ev_pivot[s->ev_used], sh.stream));
+        }
+        RC_TRY(launch_iter(s, sh, k, cap));
+        if (timed) {
+            CU_TRY(cudaEventRecord(sh.ev_pivot[s->ev_used + 1], sh.stream));
+            s->ev_used += 2;
+        }
     }
-    RC_TRY(exchange(s, (int)((k + 1) & 1), true));
+    return B200LP_OK;
+}
+
+// look(k -> k+1) (+ exchange of its candidates) on every local shard; it may start once
+// update(k-1) has produced the tableau it reads.
+static int enqueue_look(b200lp_solver *s, long long k, long long cap, bool timed = false)
+{
+    const bool multi = s->shards.size() > 1;
+    Shard &s0 = s->shards[0];
+    if (timed) {
+        while (s0.ev_lookt.size() < s->evl_used + 3) {
+            cudaEvent_t e;
+            CU_TRY(cudaEventCreate(&e));
+            s0.ev_lookt.push_back(e);
+        }
+    }
     for (Shard &sh : s->shards) {
         if (multi) CU_TRY(cudaSetDevice(sh.device));
+        if (k > 1) CU_TRY(cudaStreamWaitEvent(sh.look_stream, sh.ev_upd[(k - 1) & 3], 0));
+        if (timed && &sh == &s0) CU_TRY(cudaEventRecord(s0.ev_lookt[s->evl_used], sh.look_stream));
+        launch_look(s, sh, k, cap);
+        if (timed && &sh == &s0) CU_TRY(cudaEventRecord(s0.ev_lookt[s->evl_used + 1], sh.look_stream));
+    }
+    RC_TRY(exchange(s, (int)((k + 1) & (kRing - 1)), true));
+    for (Shard &sh : s->shards) {
+        if (multi) CU_TRY(cudaSetDevice(sh.device));
+        if (timed && &sh == &s0) {
+            CU_TRY(cudaEventRecord(s0.ev_lookt[s->evl_used + 2], sh.look_stream));
+            s->evl_used += 3;
+        }
         CU_TRY(cudaEventRecord(sh.ev_look[(k + 1) & 3], sh.look_stream));
     }
     return B200LP_OK;
@@ -504,25 +621,33 @@ static int iterate_locked(b200lp_solver *s, int64_t limit, b200lp_result *out, i
     const long long cap = limit > 0 ? start_iters + limit : 0;
     const int64_t launches0 = s->kernel_launches;
     s->ev_used = 0;
+    s->evl_used = 0;
+    const bool fused = s->xmode != 1;
+    s->epoch += 1ull << 40;                                // fresh sequence numbers for this call
     for (Shard &sh : s->shards) {
         CU_TRY(cudaSetDevice(sh.device));
         if (!sh.tabs[1]) CU_TRY(cudaMalloc(&sh.tabs[1], sizeof(double) * sh.ld * sh.R_local));
+        cudaStream_t st0 = fused ? sh.stream : sh.look_stream;
         IterState init;
         std::memset(&init, 0, sizeof(init));
         init.status = ST_START; init.j = -1; init.p = -1; init.iters = start_iters;
         Report rep;
         rep.status = ST_RUNNING; rep.pad = 0; rep.iters = start_iters;
-        CU_TRY(cudaMemcpyAsync(sh.ring, &init, sizeof(init), cudaMemcpyHostToDevice, sh.look_stream));
-        CU_TRY(cudaMemcpyAsync(sh.report, &rep, sizeof(rep), cudaMemcpyHostToDevice, sh.look_stream));
+        CU_TRY(cudaMemcpyAsync(sh.ring, &init, sizeof(init), cudaMemcpyHostToDevice, st0));
+        CU_TRY(cudaMemcpyAsync(sh.report, &rep, sizeof(rep), cudaMemcpyHostToDevice, st0));
+        CU_TRY(cudaMemsetAsync(sh.look_sync, 0, sizeof(LookSync), st0));
         CU_TRY(cudaStreamSynchronize(sh.look_stream));
         CU_TRY(cudaStreamSynchronize(sh.stream));
     }
     const bool time_pivot = s->opts.time_kernels != 0;
     const int batch = default_poll_interval(s);
     Shard &s0 = s->shards[0];
+    cudaStream_t poll_stream = fused ? s0.stream : s0.look_stream;
     CU_TRY(cudaSetDevice(s0.device));
     CU_TRY(cudaEventRecord(s0.ev_begin, s0.stream));
-    RC_TRY(enqueue_look(s, 0, cap));                       // decides iteration 1
+    // iteration 0 decides iteration 1 (fused: its update role finds nothing pending)
+    if (fused) RC_TRY(enqueue_iter(s, 0, cap, false));
+    else RC_TRY(enqueue_look(s, 0, cap));
 
     Report last;
     last.status = ST_RUNNING; last.pad = 0; last.iters = start_iters;
@@ -538,13 +663,17 @@ static int iterate_locked(b200lp_solver *s, int64_t limit, b200lp_result *out, i
             if (limit > 0) nb = std::min<long long>(batch, limit - k);
             for (long long b = 0; b < nb; ++b) {
                 ++k;
-                RC_TRY(enqueue_update(s, k, time_pivot && s->ev_used < 2 * 8192));
-                RC_TRY(enqueue_look(s, k, cap));
+                if (fused) {
+                    RC_TRY(enqueue_iter(s, k, cap, time_pivot && s->ev_used < 2 * 8192));
+                } else {
+                    RC_TRY(enqueue_update(s, k, time_pivot && s->ev_used < 2 * 8192));
+                    RC_TRY(enqueue_look(s, k, cap, time_pivot && s->evl_used < 3 * 8192));
+                }
             }
             if (s->shards.size() > 1) CU_TRY(cudaSetDevice(s0.device));
             CU_TRY(cudaMemcpyAsync(&s0.h_report[slot], s0.report, sizeof(Report),
-                                   cudaMemcpyDeviceToHost, s0.look_stream));
-            CU_TRY(cudaEventRecord(s0.ev_poll[slot], s0.look_stream));
+                                   cudaMemcpyDeviceToHost, poll_stream));
+            CU_TRY(cudaEventRecord(s0.ev_poll[slot], poll_stream));
             pending[slot] = true;
             if (limit > 0 && k >= limit) all_enqueued = true;
         }
@@ -579,6 +708,8 @@ static int iterate_locked(b200lp_solver *s, int64_t limit, b200lp_result *out, i
     CU_TRY(cudaSetDevice(s0.device));
     if (last.status == ST_RUNNING)
         return fail(B200LP_ERR_INTERNAL, "iterate", "device loop ended without a verdict");
+    if (last.status == ST_PEER_TIMEOUT)
+        return fail(B200LP_ERR_PEER_TIMEOUT, "iterate", "a peer GPU's candidate never arrived");
     const long long done = last.iters - start_iters;
     s->iters_done = last.iters;
     for (Shard &sh : s->shards) {                          // pivots ping-pong between the buffers
@@ -591,6 +722,7 @@ static int iterate_locked(b200lp_solver *s, int64_t limit, b200lp_result *out, i
         std::memset(out, 0, sizeof(*out));
         out->status = status;
         out->n_devices = s->world;
+        out->exchange_mode = s->xmode;
         out->iterations = done;
         float ms = 0.f;
         CU_TRY(cudaEventElapsedTime(&ms, s0.ev_begin, s0.ev_end));
@@ -605,6 +737,19 @@ static int iterate_locked(b200lp_solver *s, int64_t limit, b200lp_result *out, i
         }
         out->ms_pivot_kernel = pk;
         out->pivot_kernel_launches = (int64_t)real;
+        const size_t real_l = (size_t)std::min<long long>(std::max<long long>(out->iterations - 1, 0),
+                                                          (long long)(s->evl_used / 3));
+        double lk = 0.0, xk = 0.0;
+        for (size_t q = 0; q < real_l; ++q) {
+            float e = 0.f;
+            CU_TRY(cudaEventElapsedTime(&e, s0.ev_lookt[3 * q], s0.ev_lookt[3 * q + 1]));
+            lk += e;
+            CU_TRY(cudaEventElapsedTime(&e, s0.ev_lookt[3 * q + 1], s0.ev_lookt[3 * q + 2]));
+            xk += e;
+        }
+        out->ms_look_kernel = lk;
+        out->ms_exchange = xk;
+        out->look_kernel_launches = (int64_t)real_l;
         out->kernel_launches = s->kernel_launches - launches0;
         out->bytes_per_pivot = 16 * (int64_t)s0.R_local * s->C;
         double obj = 0.0;
@@ -735,6 +880,105 @@ static int download_solution_locked(b200lp_solver *s, double *rhs, double *obj_r
     return B200LP_OK;
 }
 
+// Exchange mode for a sharded solver.  Preferred: peer-mapped buffers (mode 2) -- every rank maps
+// every other rank's exchange buffer (same process: peer access; other processes: CUDA IPC
+// handles, all-gathered over the NCCL communicator that exists anyway) and k_iter's look role
+// moves the candidates itself.  Anything missing -> mode 1 (NCCL all-gather between two kernels).
+// B200LP_EXCHANGE=nccl|p2p overrides (p2p: fail instead of falling back).
+static int setup_exchange(b200lp_solver *s)
+{
+    s->xmode = 0;
+    if (s->world == 1) return B200LP_OK;
+    s->xmode = 1;
+    const char *env = getenv("B200LP_EXCHANGE");
+    const bool force_nccl = env && std::strcmp(env, "nccl") == 0;
+    const bool force_p2p = env && std::strcmp(env, "p2p") == 0;
+    if (const char *t = getenv("B200LP_PEER_TIMEOUT_MS")) {
+        const long long ms = atoll(t);
+        if (ms > 0) s->peer_timeout_ns = (unsigned long long)ms * 1000000ull;
+    }
+    if (force_nccl) return B200LP_OK;
+    bool ok = true;
+    std::string why;
+    if (!s->multiprocess) {
+        for (Shard &a : s->shards) {
+            if (cudaSetDevice(a.device) != cudaSuccess) { ok = false; break; }
+            for (Shard &b : s->shards) {
+                if (&a == &b || a.device == b.device) continue;
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, a.device, b.device) != cudaSuccess || !can) {
+                    ok = false; why = "no peer access between local devices"; break;
+                }
+                cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    ok = false; why = cudaGetErrorString(e); break;
+                }
+                (void)cudaGetLastError();
+            }
+            if (!ok) break;
+        }
+        if (ok)
+            for (Shard &a : s->shards)
+                for (Shard &b : s->shards) a.xchg.peer[b.rank] = b.xbuf;
+    } else {
+        Shard &sh = s->shards[0];
+        // all-gather (ok flag, IPC handle) through a small device buffer
+        struct Blob { cudaIpcMemHandle_t h; int ok; int pad[15]; };
+        static_assert(sizeof(Blob) == 128, "blob size");
+        std::vector<Blob> all((size_t)s->world);
+        Blob mine;
+        std::memset(&mine, 0, sizeof(mine));
+        mine.ok = cudaIpcGetMemHandle(&mine.h, sh.xbuf) == cudaSuccess ? 1 : 0;
+        (void)cudaGetLastError();
+        Blob *d = nullptr;
+        CU_TRY(cudaMalloc(&d, sizeof(Blob) * (s->world + 1)));
+        CU_TRY(cudaMemcpyAsync(d + s->world, &mine, sizeof(Blob), cudaMemcpyHostToDevice, sh.stream));
+        ncclResult_t r = g_nccl.AllGather(d + s->world, d, sizeof(Blob), ncclChar, sh.comm, sh.stream);
+        if (r != ncclSuccess) { cudaFree(d); return fail(B200LP_ERR_NCCL, "ncclAllGather(ipc)", g_nccl.GetErrorString(r)); }
+        CU_TRY(cudaMemcpyAsync(all.data(), d, sizeof(Blob) * s->world, cudaMemcpyDeviceToHost, sh.stream));
+        CU_TRY(cudaStreamSynchronize(sh.stream));
+        cudaFree(d);
+        for (int g = 0; g < s->world; ++g) ok = ok && all[(size_t)g].ok;
+        int opened_ok = 1;
+        if (ok) {
+            for (int g = 0; g < s->world && opened_ok; ++g) {
+                if (g == sh.rank) { sh.xchg.peer[g] = sh.xbuf; continue; }
+                void *ptr = nullptr;
+                cudaError_t e = cudaIpcOpenMemHandle(&ptr, all[(size_t)g].h, cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) {
+                    (void)cudaGetLastError();
+                    why = cudaGetErrorString(e);
+                    opened_ok = 0;
+                } else {
+                    sh.xchg.peer[g] = static_cast<double *>(ptr);
+                    sh.ipc_opened[g] = true;
+                }
+            }
+        } else {
+            why = "cudaIpcGetMemHandle failed on some rank";
+            opened_ok = 0;
+        }
+        // every rank must take the same path: agree (min) on success through one more all-gather
+        int *dflag = nullptr;
+        CU_TRY(cudaMalloc(&dflag, sizeof(int) * (s->world + 1)));
+        CU_TRY(cudaMemcpyAsync(dflag + s->world, &opened_ok, sizeof(int), cudaMemcpyHostToDevice, sh.stream));
+        r = g_nccl.AllGather(dflag + s->world, dflag, sizeof(int), ncclChar, sh.comm, sh.stream);
+        if (r != ncclSuccess) { cudaFree(dflag); return fail(B200LP_ERR_NCCL, "ncclAllGather(ipc ok)", g_nccl.GetErrorString(r)); }
+        std::vector<int> flags((size_t)s->world);
+        CU_TRY(cudaMemcpyAsync(flags.data(), dflag, sizeof(int) * s->world, cudaMemcpyDeviceToHost, sh.stream));
+        CU_TRY(cudaStreamSynchronize(sh.stream));
+        cudaFree(dflag);
+        ok = true;
+        for (int g = 0; g < s->world; ++g) ok = ok && flags[(size_t)g];
+    }
+    if (ok) {
+        s->xmode = 2;
+        return B200LP_OK;
+    }
+    if (force_p2p) return fail(B200LP_ERR_CUDA, "peer-mapped exchange unavailable", why.c_str());
+    return B200LP_OK;
+}
+
 static int create_common(const b200lp_opts *opts, int64_t R, int64_t C, int32_t is_max,
                          b200lp_solver **out)
 {
@@ -816,6 +1060,7 @@ const char *b200lp_strerror(int code)
     case B200LP_ERR_NO_DEVICE: return "no CUDA device";
     case B200LP_ERR_OUT_OF_MEMORY: return "out of device memory";
     case B200LP_ERR_INTERNAL: return "internal error";
+    case B200LP_ERR_PEER_TIMEOUT: return "timed out waiting for a peer GPU";
     default: return "unknown status";
     }
 }
@@ -856,6 +1101,7 @@ int b200lp_create(const b200lp_opts *opts, int64_t R, int64_t C, int32_t is_max,
                 else for (int g = 0; g < nd; ++g) s->shards[g].comm = comms[g];
             }
         }
+        if (!rc) rc = setup_exchange(s);
         if (rc) { b200lp_destroy(s); *out = nullptr; return rc; }
         return B200LP_OK;
     } catch (const std::exception &ex) {
@@ -906,6 +1152,7 @@ int b200lp_create_sharded(const b200lp_opts *opts, int64_t R, int64_t C, int32_t
                 if (r != ncclSuccess) rc = fail(B200LP_ERR_NCCL, "ncclCommInitRank", g_nccl.GetErrorString(r));
             }
         }
+        if (!rc) rc = setup_exchange(s);
         if (rc) { b200lp_destroy(s); *out = nullptr; return rc; }
         return B200LP_OK;
     } catch (const std::exception &ex) {

@@ -39,7 +39,8 @@
   (iterations-cleanup :int64) (objective :double) (ms-total :double) (ms-h2d :double)
   (ms-solve :double) (ms-d2h :double) (ms-pivot-kernel :double) (pivot-kernel-launches :int64)
   (kernel-launches :int64) (h2d-bytes :int64) (d2h-bytes :int64) (bytes-per-pivot :int64)
-  (trace-len :int32) (reserved :int32))
+  (trace-len :int32) (exchange-mode :int32) (ms-look-kernel :double) (ms-exchange :double)
+  (look-kernel-launches :int64))
 
 (cffi:defcfun ("b200lp_solve" %solve) :int
   (opts :pointer) (tab :pointer) (r :int64) (c :int64) (ld :int64) (basis :pointer)
