@@ -140,6 +140,10 @@ int b200lp_pivot(b200lp_solver *s, int64_t entering_col, int64_t changing_row);
 int b200lp_iterate(b200lp_solver *s, int64_t max_iters, b200lp_result *out,
                    int32_t *trace_j, int32_t *trace_r);
 
+/* Turn per-launch CUDA-event timing (opts.time_kernels) on or off for later b200lp_iterate calls.
+ * Timing events between launches serialise consecutive iterations, so throughput runs keep it off. */
+int b200lp_set_time_kernels(b200lp_solver *s, int32_t on);
+
 /* ---- multi-process row-block sharding (one process per GPU, NCCL over NVLink) ---------------
  * Rank g owns constraint rows [row_begin, row_end) plus a replica of the objective row; the
  * per-iteration exchange is one all-gather of each rank's candidate pivot row.  `unique_id` is

@@ -102,6 +102,7 @@ SIGNATURES = {
     "b200lp_find_pivoting_row": (ctypes.c_int, [_vp, ctypes.c_int64, _lp]),
     "b200lp_pivot": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64]),
     "b200lp_iterate": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.POINTER(Result), _ip, _ip]),
+    "b200lp_set_time_kernels": (ctypes.c_int, [_vp, ctypes.c_int32]),
     "b200lp_comm_unique_id": (ctypes.c_int, [_vp]),
     "b200lp_create_sharded": (ctypes.c_int, [ctypes.POINTER(Opts), ctypes.c_int64, ctypes.c_int64,
                                              ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp,
@@ -315,6 +316,9 @@ class DeviceTableau:
 
     def pivot(self, j, r):
         _check(lib().b200lp_pivot(self._h, int(j), int(r)), "b200lp_pivot")
+
+    def set_time_kernels(self, on):
+        _check(lib().b200lp_set_time_kernels(self._h, int(bool(on))), "b200lp_set_time_kernels")
 
     def iterate(self, max_iters=0):
         """Returns (status, Result, trace)."""

@@ -391,8 +391,9 @@ struct alignas(16) Report {   // what the host polls
 struct alignas(16) LookSync {
     unsigned int bar[4];
     unsigned int fail;
-    unsigned int tile_ctr[2];
-    unsigned int pad;
+    unsigned int look_count;              // telemetry: look roles that ran to a decision
+    unsigned long long look_t0;           //            %globaltimer at the start of the current one
+    unsigned long long look_ns;           //            summed duration
     Cand part_enter[kLookMaxCtas];
     Cand part_ratio[kLookMaxCtas];
 };
@@ -530,9 +531,7 @@ __device__ __forceinline__ void look_role(const LookArgs &A, const int cta, cons
     const int tid = threadIdx.x;
     const IterState st = A.ring[A.slot_in];
     IterState *st_out = A.ring + A.slot_out;
-    if (cta == 0 && tid == 0) {                                // re-arm next iteration's tile counter
-        A.sync->tile_ctr[A.slot_out & 1] = 0;
-    }
+    if (cta == 0 && tid == 0) A.sync->look_t0 = global_timer_ns();
     if (st.status != ST_RUNNING && st.status != ST_START) {   // solve already over: pass it on
         if (cta == 0 && tid == 0) *st_out = st;
         return;
@@ -769,6 +768,8 @@ __device__ __forceinline__ void look_role(const LookArgs &A, const int cta, cons
         A.report->status = o.status;
     }
     *st_out = o;
+    A.sync->look_ns += global_timer_ns() - *reinterpret_cast<volatile unsigned long long *>(&A.sync->look_t0);
+    A.sync->look_count += 1;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -787,7 +788,6 @@ struct UpdateArgs {
     const double *gathring;   // mode 1
     int64_t cand_stride;
     const double *xrow;       // mode 2: this rank's xchg row ring base (slot 0)
-    unsigned int *tile_ctr;   // k_iter only
 };
 
 // Which row is the pivot row and where its scaled copy lives; false = nothing to apply.
@@ -880,6 +880,11 @@ template <int TR, int UNROLL, bool STREAM>
 __global__ void __launch_bounds__(kPivotThreads, UNROLL >= 16 ? 2 : 4)
 k_iter(const LookArgs A, const UpdateArgs U, const int look_ctas)
 {
+    // Programmatic dependent launch: this grid may be made resident while the previous
+    // iteration's grid drains; nothing it produced is touched before the wait, and the next
+    // iteration's grid is allowed to queue up behind this one right away.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
     if ((int)blockIdx.x < look_ctas) {
         look_role(A, blockIdx.x, look_ctas);
         return;

@@ -32,6 +32,10 @@ namespace b200lp {
 static constexpr double kClEps = 0x1.0000000000001p-53;
 
 static thread_local std::string g_last_error;
+static const bool g_use_pdl = []() {
+    const char *e = getenv("B200LP_PDL");       // default on; B200LP_PDL=0 serialises iterations
+    return !(e && e[0] == '0');
+}();
 static NcclApi g_nccl;
 static std::mutex g_nccl_mu;
 
@@ -432,7 +436,6 @@ static void fill_args(b200lp_solver *s, Shard &sh, long long k, long long cap, L
     u->ring = sh.ring; u->colring = sh.colring; u->col_stride = sh.R_local;
     u->candring = sh.candring; u->gathring = sh.gathring; u->cand_stride = stride;
     u->xrow = sh.xbuf ? sh.xbuf + xchg_row_off(0, sh.ld) : nullptr;
-    u->tile_ctr = &sh.look_sync->tile_ctr[slot & 1];
 }
 
 static int pick_variant(const b200lp_solver *s, const Shard &sh)
@@ -440,10 +443,10 @@ static int pick_variant(const b200lp_solver *s, const Shard &sh)
     int v = s->opts.pivot_variant;
     if (v == 0) {
         // Two ping-pong buffers that fit the 126 MB L2 keep default caching; larger tableaus
-        // stream with the deepest load batch (16 rows in flight per thread: best on B200 at
-        // every size > L2, profiles/r01_variant_sweep_*.json).
+        // stream in 16-row tiles with all 16 loads of a thread in flight before its first store
+        // (best on B200 at every size > L2: least tail, profiles/r01_variant_sweep_*.json).
         const double bytes = 8.0 * (double)sh.ld * sh.R_local;
-        v = bytes > 48e6 ? 6 : 2;
+        v = bytes > 48e6 ? 10 : 2;
     }
     return v;
 }
@@ -461,6 +464,10 @@ static int pick_variant(const b200lp_solver *s, const Shard &sh)
     case 7: X(128, 8, true); break;    \
     case 8: X(64, 4, true); break;     \
     case 9: X(128, 16, false); break;  \
+    case 10: X(16, 16, true); break;   \
+    case 11: X(32, 16, true); break;   \
+    case 12: X(32, 8, false); break;   \
+    case 13: X(16, 8, true); break;    \
     }
 
 template <int TR, int UNROLL, bool STREAM>
@@ -471,8 +478,16 @@ static cudaError_t launch_iter_t(Shard &sh, const LookArgs &a, const UpdateArgs 
         const int64_t ntiles = ((ldv + kPivotThreads - 1) / kPivotThreads) * ((sh.R_local + TR - 1) / TR);
         sh.iter_ctas = sh.look_ctas + (int)ntiles;
     }
-    k_iter<TR, UNROLL, STREAM><<<sh.iter_ctas, kPivotThreads, 0, sh.stream>>>(a, u, sh.look_ctas);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)sh.iter_ctas);
+    cfg.blockDim = dim3(kPivotThreads);
+    cfg.stream = sh.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_iter<TR, UNROLL, STREAM>, a, u, sh.look_ctas);
 }
 
 static int launch_iter(b200lp_solver *s, Shard &sh, long long k, long long cap)
@@ -750,6 +765,12 @@ static int iterate_locked(b200lp_solver *s, int64_t limit, b200lp_result *out, i
         out->ms_look_kernel = lk;
         out->ms_exchange = xk;
         out->look_kernel_launches = (int64_t)real_l;
+        if (fused) {                                       // timed on the device by the look role
+            LookSync ls;
+            CU_TRY(cudaMemcpy(&ls, s0.look_sync, sizeof(ls), cudaMemcpyDeviceToHost));
+            out->ms_look_kernel = (double)ls.look_ns * 1e-6;
+            out->look_kernel_launches = ls.look_count;
+        }
         out->kernel_launches = s->kernel_launches - launches0;
         out->bytes_per_pivot = 16 * (int64_t)s0.R_local * s->C;
         double obj = 0.0;
@@ -1250,6 +1271,14 @@ int b200lp_iterate(b200lp_solver *s, int64_t max_iters, b200lp_result *out, int3
     } catch (const std::exception &ex) {
         return fail(B200LP_ERR_INTERNAL, "iterate", ex.what());
     }
+}
+
+int b200lp_set_time_kernels(b200lp_solver *s, int32_t on)
+{
+    if (!s) return fail(B200LP_ERR_INVALID_ARG, "set_time_kernels", "null solver");
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->opts.time_kernels = on ? 1 : 0;
+    return B200LP_OK;
 }
 
 int b200lp_solve(const b200lp_opts *opts, double *tab, int64_t R, int64_t C, int64_t ld,

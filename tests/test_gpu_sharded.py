@@ -26,10 +26,15 @@ needs2 = pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
 
 
 @needs2
+@pytest.mark.parametrize("exchange,mode", [("p2p", 2), ("nccl", 1)])
 @pytest.mark.parametrize("ndev,m,n", [(2, 200, 300), (2, 33, 20), (4, 130, 257), (8, 64, 96)])
-def test_in_process_multi_device_bit_exact(ndev, m, n):
+def test_in_process_multi_device_bit_exact(ndev, m, n, exchange, mode, monkeypatch):
+    """Both ways the candidate pivot rows travel: peer-mapped buffers written inside the
+    iteration kernel (default) and the NCCL all-gather fallback."""
     if _ngpu() < ndev:
         pytest.skip(f"needs {ndev} GPUs")
+    monkeypatch.setenv("B200LP_EXCHANGE", exchange)
+    monkeypatch.setenv("B200LP_PEER_TIMEOUT_MS", "5000")
     tab, basis = synthetic.dense_tableau(m, n, seed=13)
     o_tab, o_basis = tab.copy(), basis.copy()
     ost, oit, otrace = oracle.solve(o_tab, o_basis, True, trace_cap=1 << 16)
@@ -37,24 +42,27 @@ def test_in_process_multi_device_bit_exact(ndev, m, n):
                                 _ffi.make_opts(devices=list(range(ndev)), writeback_full=True,
                                                trace_capacity=1 << 16))
     assert st == ost and res.iterations == oit and res.n_devices == ndev
+    assert res.exchange_mode == mode
     assert trace == otrace
     assert np.array_equal(tab, o_tab) and np.array_equal(basis, o_basis)
 
 
-def _torchrun(nproc, *args):
+def _torchrun(nproc, *args, exchange="p2p"):
+    env = dict(os.environ, B200LP_EXCHANGE=exchange, B200LP_PEER_TIMEOUT_MS="5000")
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "sharded_worker.py"), *map(str, args)]
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
 
 
 @needs2
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
 @pytest.mark.parametrize("args", [(300, 500), (128, 128, 1, "degenerate"), (128, 128, 0, "degenerate")])
-def test_one_process_per_gpu_nccl(args):
-    out = _torchrun(2, *args)
+def test_one_process_per_gpu(args, exchange):
+    out = _torchrun(2, *args, exchange=exchange)
     assert out.returncode == 0 and "SHARDED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 

@@ -25,17 +25,18 @@ def main():
     R, C = tab.shape
     rows = []
     for v in variants:
-        opts = _ffi.make_opts(time_kernels=True, pivot_variant=v)
+        opts = _ffi.make_opts(time_kernels=os.environ.get('SWEEP_TIME_KERNELS', '1') != '0', pivot_variant=v)
         with _ffi.DeviceTableau(R, C, True, opts) as d:
             t0 = time.time()
             d.upload(tab, basis)
             up = time.time() - t0
             d.iterate(5)
             st, res, _ = d.iterate(40)
-            per = res.ms_pivot_kernel / max(res.pivot_kernel_launches, 1)
+            per = res.ms_pivot_kernel / max(res.pivot_kernel_launches, 1) or res.ms_solve / res.iterations
             row = dict(variant=v, pivots=res.iterations, ms_iter=res.ms_solve / res.iterations,
                        ms_pivot=per, gbs=16.0 * R * C / per / 1e6,
                        pivots_per_s=1e3 * res.iterations / res.ms_solve, upload_s=round(up, 3),
+                       us_look=1e3 * res.ms_look_kernel / max(res.look_kernel_launches, 1),
                        launches=res.kernel_launches)
             rows.append(row)
             print(json.dumps(row), flush=True)
