@@ -277,7 +277,10 @@ def run_b200(args, cfg, workload):
                                                                    max_iters=args.e2e_max_iters))
             iters = int(r2.iterations)
             h2d, d2h = int(r2.h2d_bytes), int(r2.d2h_bytes)
+            breakdown = {"ms_h2d": r2.ms_h2d, "ms_solve": r2.ms_solve, "ms_d2h": r2.ms_d2h,
+                         "ms_total_in_call": r2.ms_total}
         else:
+            breakdown = None
             dev.upload(blk, blk_basis)
             st2, r2, _ = dev.iterate(args.e2e_max_iters)
             dev.download_solution()
@@ -288,7 +291,7 @@ def run_b200(args, cfg, workload):
         wall = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": iters / wall, "unit": UNIT,
                "h2d_bytes_per_step": h2d / max(iters, 1), "d2h_bytes_per_step": d2h / max(iters, 1),
-               "pivots": iters, "wall_s": wall, "status": int(st2),
+               "pivots": iters, "wall_s": wall, "status": int(st2), "breakdown": breakdown,
                "what": "one solve call: pinned host tableau H2D + all pivots + solution D2H"}
     dev.close()
 

@@ -927,6 +927,19 @@ __global__ void k_gather_col(const double *__restrict__ tab, int64_t ld, int R_l
     if (i < R_local) out[i] = tab[(int64_t)i * ld + col];
 }
 
+// Upload staging: a host tableau with ld == C crosses PCIe as ONE contiguous copy into the spare
+// ping-pong buffer and is re-pitched here to the padded device row stride (pads zeroed).
+__global__ void k_repitch(const double *__restrict__ src, int64_t C, double *__restrict__ dst,
+                          int64_t ld, int R_local)
+{
+    const int64_t n = (int64_t)R_local * ld;
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n;
+         k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = k / ld, c = k - r * ld;
+        dst[k] = c < C ? src[r * C + c] : 0.0;
+    }
+}
+
 __global__ void k_zero_pad(double *__restrict__ tab, int64_t ld, int R_local, int C)
 {
     const int pad = (int)ld - C;

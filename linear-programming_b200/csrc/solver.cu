@@ -800,29 +800,36 @@ static int upload_locked(b200lp_solver *s, const double *tab, int64_t ld, const 
 {
     if (!tab || ld < s->C) return fail(B200LP_ERR_INVALID_ARG, "upload", "ld < C or null tableau");
     const size_t wbytes = sizeof(double) * s->C;
+    const bool contiguous = ld == s->C && s->C != s->shards[0].ld;
     for (Shard &sh : s->shards) {
         CU_TRY(cudaSetDevice(sh.device));
-        if (s->multiprocess || s->shards.size() == 1) {
-            // local block: R_local rows, objective last
-            CU_TRY(cudaMemcpy2DAsync(sh.tab, sizeof(double) * sh.ld, tab, sizeof(double) * ld,
-                                     wbytes, sh.R_local, cudaMemcpyHostToDevice, sh.stream));
-            if (basis && sh.m_local > 0)
-                CU_TRY(cudaMemcpyAsync(sh.basis, basis, sizeof(int32_t) * sh.m_local,
-                                       cudaMemcpyHostToDevice, sh.stream));
-        } else {
-            // in-process sharding: scatter row blocks of the full tableau, replicate the objective
+        const bool local = s->multiprocess || s->shards.size() == 1;
+        const double *rows = local ? tab : tab + sh.row0 * ld;       // this shard's constraint rows
+        const double *obj = local ? tab + (int64_t)sh.m_local * ld : tab + s->m * ld;
+        if (contiguous) {
+            // one contiguous DMA per shard (a pitched 2-D copy of odd-width rows runs at a fraction
+            // of PCIe speed), staged in the spare ping-pong buffer, then re-pitched on the device
+            const int other = sh.cur ^ 1;
+            if (!sh.tabs[other])
+                CU_TRY(cudaMalloc(&sh.tabs[other], sizeof(double) * sh.ld * sh.R_local));
+            double *stage = sh.tabs[other];
             if (sh.m_local > 0)
-                CU_TRY(cudaMemcpy2DAsync(sh.tab, sizeof(double) * sh.ld, tab + sh.row0 * ld,
-                                         sizeof(double) * ld, wbytes, sh.m_local,
-                                         cudaMemcpyHostToDevice, sh.stream));
-            CU_TRY(cudaMemcpyAsync(sh.tab + (int64_t)sh.m_local * sh.ld, tab + s->m * ld, wbytes,
+                CU_TRY(cudaMemcpyAsync(stage, rows, wbytes * sh.m_local, cudaMemcpyHostToDevice, sh.stream));
+            CU_TRY(cudaMemcpyAsync(stage + (int64_t)sh.m_local * s->C, obj, wbytes,
                                    cudaMemcpyHostToDevice, sh.stream));
-            if (basis && sh.m_local > 0)
-                CU_TRY(cudaMemcpyAsync(sh.basis, basis + sh.row0, sizeof(int32_t) * sh.m_local,
-                                       cudaMemcpyHostToDevice, sh.stream));
+            k_repitch<<<148 * 8, 256, 0, sh.stream>>>(stage, s->C, sh.tab, sh.ld, sh.R_local);
+        } else {
+            if (sh.m_local > 0)
+                CU_TRY(cudaMemcpy2DAsync(sh.tab, sizeof(double) * sh.ld, rows, sizeof(double) * ld,
+                                         wbytes, sh.m_local, cudaMemcpyHostToDevice, sh.stream));
+            CU_TRY(cudaMemcpyAsync(sh.tab + (int64_t)sh.m_local * sh.ld, obj, wbytes,
+                                   cudaMemcpyHostToDevice, sh.stream));
+            if (sh.ld > s->C)
+                k_zero_pad<<<64, 256, 0, sh.stream>>>(sh.tab, sh.ld, sh.R_local, (int)s->C);
         }
-        if (sh.ld > s->C)
-            k_zero_pad<<<64, 256, 0, sh.stream>>>(sh.tab, sh.ld, sh.R_local, (int)s->C);
+        if (basis && sh.m_local > 0)
+            CU_TRY(cudaMemcpyAsync(sh.basis, basis + (local ? 0 : sh.row0), sizeof(int32_t) * sh.m_local,
+                                   cudaMemcpyHostToDevice, sh.stream));
     }
     for (Shard &sh : s->shards) {
         CU_TRY(cudaSetDevice(sh.device));

@@ -307,3 +307,47 @@ def test_invalid_arguments_raise_not_crash():
             d.find_pivoting_row(10 ** 6)
     with pytest.raises(_ffi.B200DeviceError):
         _ffi.DeviceTableau(1, 1)
+
+
+# ------------------------------------------------------------------ BASELINE.json's full sizes
+def _basis_columns_are_unit_vectors(tab, basis):
+    """Size-independent invariant of n-pivot-row (src/simplex.lisp:344-357): after any number of
+    pivots the basic column of row i is EXACTLY e_i (x/x = 1, a - a*1 = 0), objective row included."""
+    m = tab.shape[0] - 1
+    cols = tab[:, basis]                                   # (m+1) x m
+    want = np.zeros_like(cols)
+    want[np.arange(m), np.arange(m)] = 1.0
+    return np.array_equal(cols, want)
+
+
+@pytest.mark.parametrize("m,n,degenerate,rule,k_exact", [
+    (8192, 16384, False, 0, 10),       # config 3
+    (4096, 4096, True, 0, 150),        # config 5, reference rule
+    (4096, 4096, True, 1, 150),        # config 5, Bland
+    (16384, 32768, False, 0, 3),       # config 4 on one GPU
+])
+def test_full_size_configs_prefix_bit_exact_then_invariants(m, n, degenerate, rule, k_exact):
+    tab, basis = synthetic.dense_tableau(m, n, seed=1234, degenerate=degenerate)
+    o_tab, o_basis = tab.copy(), basis.copy()
+    ost, oit, otrace = oracle.solve(o_tab, o_basis, True, rule=rule, max_iters=k_exact,
+                                    parallel=True, trace_cap=k_exact)
+    opts = _ffi.make_opts(pivot_rule=rule, trace_capacity=4096)
+    with _ffi.DeviceTableau(*tab.shape, opts=opts) as d:
+        d.upload(tab, basis)
+        st, res, trace = d.iterate(k_exact)
+        assert (st, res.iterations) == (ost, oit) and trace == otrace
+        rhs, obj, g_basis = d.download_solution()
+        assert np.array_equal(rhs, o_tab[:, -1]) and np.array_equal(obj, o_tab[-1])
+        assert np.array_equal(g_basis, o_basis)
+        del o_tab
+        # keep going well past what the CPU can check cell by cell
+        before = res.objective
+        st, res, trace = d.iterate(400)
+        assert st in (_ffi.ITERATION_LIMIT, _ffi.OK)
+        assert res.objective >= before                      # max problem: never decreases
+        full, g_basis = d.download()
+    assert len(set(g_basis.tolist())) == m                  # a basis: m distinct columns
+    assert _basis_columns_are_unit_vectors(full, g_basis)
+    assert full[-1, -1] == res.objective
+    if not degenerate:
+        assert (full[:-1, -1] >= -1e-9).all()               # primal feasibility is kept
