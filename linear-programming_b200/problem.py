@@ -12,6 +12,11 @@ from .sexp import as_form
 _gensym = itertools.count()
 
 
+class Uninterned(str):
+    """An objective-variable name nobody wrote down: (gensym "Z") in parse-linear-problem
+    (src/problem.lisp:167) or (make-symbol objective) in read-mps.  write-sexp leaves these out."""
+
+
 @dataclass
 class Problem:
     """src/problem.lisp:45-53.  constraints: [(op, [(var, coef)...], rhs)] with op in <=, >=, =;
@@ -120,7 +125,7 @@ def parse_linear_problem(objective_exp, constraints):
     constraints = [as_form(c) for c in constraints]
     has_var = objective_exp[0] == "="
     objective = objective_exp[2] if has_var else objective_exp
-    objective_var = objective_exp[1] if has_var else f"z{next(_gensym)}"
+    objective_var = objective_exp[1] if has_var else Uninterned(f"z{next(_gensym)}")
     if (not has_var and isinstance(objective[1], list) and objective[1] and objective[1][0] == "="):
         objective_var = objective[1][1]
         objective = [objective[0], objective[1][2]]
