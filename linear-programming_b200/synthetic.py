@@ -7,19 +7,21 @@ The tableau is what the reference's build-tableau produces for such a problem
 import numpy as np
 
 
-def dense_lp(m, n, seed=1234, degenerate=False):
+def dense_lp(m, n, seed=1234, degenerate=False, zero_frac=0.5):
     """A ~ U[0,1), b ~ U[n/8, 3n/8), c ~ U[0,1).
 
     degenerate=True is config 5: small-integer data with exact ratio ties.  The first half of
     the rows are cone constraints through the origin (A in {-1,0,1}, b = 0: every ratio there
     is exactly 0, so the leaving row is decided by the tie-break alone); the second half
-    (A in {0,1,2}, b in {n/4, n/2, 3n/4}) bounds the polytope; c in {1,2,3}."""
+    (A in {0,1,2}, b in {n/4, n/2, 3n/4}) bounds the polytope; c in {1,2,3}.  `zero_frac` is the
+    share of cone rows: 1/2 stalls for millions of pivots at m = 4096 (prefix-parity use), 1/32 still
+    produces thousands of exact ties but solves in ~10^4 pivots."""
     rng = np.random.default_rng(seed)
     if degenerate:
         A = rng.integers(0, 3, size=(m, n)).astype(np.float64)
         b = rng.integers(1, 4, size=m).astype(np.float64) * n / 4.0
         c = rng.integers(1, 4, size=n).astype(np.float64)
-        half = m // 2
+        half = int(m * zero_frac)
         A[:half] = rng.integers(-1, 2, size=(half, n))
         b[:half] = 0.0
         return A, b, c
@@ -44,8 +46,8 @@ def tableau_from_lp(A, b, c, out=None):
     return tab, basis
 
 
-def dense_tableau(m, n, seed=1234, degenerate=False, out=None):
-    A, b, c = dense_lp(m, n, seed, degenerate)
+def dense_tableau(m, n, seed=1234, degenerate=False, out=None, zero_frac=0.5):
+    A, b, c = dense_lp(m, n, seed, degenerate, zero_frac)
     return tableau_from_lp(A, b, c, out=out)
 
 

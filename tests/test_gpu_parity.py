@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from golden import reference_goldens as G
+from lp_checks import certify_optimal
 from linear_programming_b200 import _ffi, synthetic
 from oracle import oracle
 
@@ -351,3 +352,31 @@ def test_full_size_configs_prefix_bit_exact_then_invariants(m, n, degenerate, ru
     assert full[-1, -1] == res.objective
     if not degenerate:
         assert (full[:-1, -1] >= -1e-9).all()               # primal feasibility is kept
+
+
+@pytest.mark.parametrize("m,n,degenerate", [(1024, 2048, False), (8192, 16384, False),
+                                            (4096, 4096, True)])
+def test_full_solve_is_certified_optimal_at_baseline_sizes(m, n, degenerate):
+    """Configs 2, 3 and 5 (moderately degenerate variant) solved to optimality through
+    b200lp_solve, then certified by LP duality on the CPU."""
+    A, b, c = synthetic.dense_lp(m, n, seed=1234, degenerate=degenerate, zero_frac=1 / 32)
+    tab, basis = synthetic.tableau_from_lp(A, b, c)
+    st, res, _ = _ffi.solve(tab, basis, True, _ffi.make_opts(max_iters=400000))
+    assert st == _ffi.OK
+    value = certify_optimal(A, b, c, tab[:, -1], tab[-1], basis)
+    assert value == res.objective
+    if (m, n) == (1024, 2048):
+        assert abs(value - 545.8113461511593) <= 1e-8 * 545.8113461511593      # HiGHS, SURVEY 6
+
+
+@pytest.mark.parametrize("m,rule", [(1024, 0), (512, 1)])
+def test_degenerate_full_solve_final_basis_bit_exact(m, rule):
+    """Thousands of exact ratio ties, solved to the end under both rules: the final basis, the
+    whole tableau and the pivot count equal the oracle's."""
+    tab, basis = synthetic.dense_tableau(m, m, seed=1234, degenerate=True, zero_frac=1 / 32)
+    o_tab, o_basis = tab.copy(), basis.copy()
+    ost, oit, _ = oracle.solve(o_tab, o_basis, True, rule=rule, max_iters=400000, parallel=True)
+    st, res, _ = _ffi.solve(tab, basis, True, _ffi.make_opts(pivot_rule=rule, max_iters=400000,
+                                                             writeback_full=True))
+    assert st == ost == _ffi.OK and res.iterations == oit
+    assert np.array_equal(basis, o_basis) and np.array_equal(tab, o_tab)

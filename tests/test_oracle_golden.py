@@ -201,3 +201,15 @@ def test_c_bland_on_beale():
     tab, basis = f64(g["matrix"]), i32(g["basis"])
     st, it, _ = oracle.solve(tab, basis, True, rule=1, max_iters=600)
     assert st == oracle.OPTIMAL and abs(tab[-1, -1] - 0.05) < 1e-12
+
+
+@pytest.mark.parametrize("m,n,degenerate", [(200, 300, False), (256, 256, True)])
+def test_c_oracle_optimum_is_certified_by_duality(m, n, degenerate):
+    """Independent of any golden: primal + dual feasibility and a closed duality gap."""
+    from lp_checks import certify_optimal
+    from linear_programming_b200 import synthetic
+    A, b, c = synthetic.dense_lp(m, n, seed=3, degenerate=degenerate, zero_frac=1 / 32)
+    tab, basis = synthetic.tableau_from_lp(A, b, c)
+    st, _, _ = oracle.solve(tab, basis, True, max_iters=200000)
+    assert st == oracle.OPTIMAL
+    certify_optimal(A, b, c, tab[:, -1], tab[-1], basis)
