@@ -139,7 +139,7 @@ def run_reference(args, cfg, workload):
     m, n = cfg["m"], cfg["n"]
     tab, basis = synthetic.dense_tableau(m, n, degenerate=cfg["degenerate"])
     R, C = tab.shape
-    cores = oracle.num_threads()
+    cores = oracle.set_num_threads(len(os.sched_getaffinity(0)))
     budget_s = 150.0
     t_start = time.time()
 
@@ -300,6 +300,7 @@ def run_b200(args, cfg, workload):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle
         oracle.build()
+        oracle.set_num_threads(len(os.sched_getaffinity(0)))
         tab2, basis2 = synthetic.dense_tableau(m, n, degenerate=cfg["degenerate"], out=tab)
         n_cpu, t_budget = 0, 20.0
         for k in range(2):   # warm-up
@@ -316,6 +317,17 @@ def run_b200(args, cfg, workload):
         cpu = {"value": n_cpu / dt, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
                "sample": f"{n_cpu} pivots of the full {R}x{C} tableau after 2 warm-up pivots "
                          f"(oracle C port, OpenMP over rows; the Lisp reference cannot run here)"}
+        # the reference itself is single-threaded: the same port on one core, 3 pivots
+        t0 = time.perf_counter()
+        n1 = 0
+        while n1 < 3:
+            j = oracle.find_entering_column(tab2, True)
+            if j < 0:
+                break
+            oracle.pivot(tab2, basis2, j, oracle.find_pivoting_row(tab2, basis2, j), parallel=False)
+            n1 += 1
+        cpu["single_core"] = {"value": n1 / (time.perf_counter() - t0), "unit": UNIT, "cores": 1,
+                              "sample": f"{n1} pivots, same tableau, one thread"}
 
     if rank == 0:
         peak, peak_src = load_peak()

@@ -1342,8 +1342,14 @@ int b200lp_solve_two_phase(const b200lp_opts *opts, double *art_tab, int64_t C_a
 {
     if (!art_tab || !art_basis || !main_tab || !main_basis || ld_art < C_art || ld < C || C_art < C)
         return fail(B200LP_ERR_INVALID_ARG, "solve_two_phase", "null buffer or bad dimensions");
-    if (opts && opts->ndev > 1)
-        return fail(B200LP_ERR_INVALID_ARG, "solve_two_phase", "two-phase runs on one device");
+    // The phase transition re-prices the objective row over ALL rows in order (:444-451), so the
+    // two-phase variant runs on one GPU: with several devices requested it uses devices[0].
+    b200lp_opts one;
+    if (opts && opts->ndev > 1) {
+        one = *opts;
+        one.ndev = 0;
+        opts = &one;
+    }
     const double t0 = now_ms();
     b200lp_solver *art = nullptr, *mn = nullptr;
     b200lp_result r1, r2;

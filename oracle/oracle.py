@@ -85,6 +85,12 @@ def num_threads():
     return lib().oracle_num_threads()
 
 
+def set_num_threads(n):
+    """All host cores for the CPU-baseline legs (torchrun pins OMP_NUM_THREADS=1)."""
+    lib().oracle_set_num_threads(int(n))
+    return num_threads()
+
+
 def find_entering_column(tab, is_max, tol=1024.0, rule=0):
     R, C, ld = _check_tab(tab)
     return int(lib().oracle_find_entering_column(_dp(tab), R, C, ld, int(is_max), tol, rule))

@@ -53,6 +53,17 @@ int oracle_num_threads(void)
 #endif
 }
 
+/* Threads for the OpenMP-over-rows pivot (CPU baseline only; results do not depend on it).
+ * torchrun exports OMP_NUM_THREADS=1, so the bench sets the count explicitly. */
+void oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* find-entering-column, src/simplex.lisp:362-379.
  * max problem: first argmin of the objective row over [0, var_count); accept iff
  * value < 0 - (tol/8)*eps.  min problem: first argmax; accept iff > 0 + (tol/8)*eps.

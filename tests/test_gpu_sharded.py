@@ -70,3 +70,17 @@ def test_one_process_per_gpu(args, exchange):
 def test_eight_ranks():
     out = _torchrun(8, 1000, 1500)
     assert out.returncode == 0 and "SHARDED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+@needs2
+def test_two_phase_with_several_devices_requested_runs_on_the_first():
+    """b200lp_solve_two_phase is single-GPU by contract (include/b200lp.h); asking for more
+    devices must still solve, not fail."""
+    from golden import reference_goldens as G
+    g = G.EQ_SOLVED
+    b = g["initial"]
+    f64 = lambda rows: np.array([[float(x) for x in r] for r in rows])     # noqa: E731
+    art, ab = f64(b["art_matrix"]), np.array(b["art_basis"], np.int32)
+    main, mb = f64(b["main_matrix"]), np.array(b["main_basis"], np.int32)
+    st, res = _ffi.solve_two_phase(art, ab, main, mb, True, _ffi.make_opts(devices=[0, 1]))
+    assert st == _ffi.OK and res.objective == 28.5 and mb.tolist() == g["main_basis"]
