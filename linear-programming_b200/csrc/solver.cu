@@ -38,6 +38,11 @@ static const bool g_use_pdl = []() {
 }();
 static NcclApi g_nccl;
 static std::mutex g_nccl_mu;
+// One pipelined loop per GPU at a time: the lookahead CTAs of k_iter meet at grid barriers and
+// must not compete for SM slots with another handle's tiles.  Different handles on the same
+// device therefore serialise at b200lp_iterate granularity ("serialise rather than corrupt").
+static constexpr int kMaxDeviceLocks = 64;
+static std::mutex g_device_mu[kMaxDeviceLocks];
 
 static int fail(int code, const char *what, const char *detail)
 {
@@ -1273,6 +1278,15 @@ int b200lp_iterate(b200lp_solver *s, int64_t max_iters, b200lp_result *out, int3
 {
     if (!s) return fail(B200LP_ERR_INVALID_ARG, "iterate", "null solver");
     std::lock_guard<std::mutex> lk(s->mu);
+    std::vector<int> devs;
+    for (const Shard &sh : s->shards) devs.push_back(((sh.device % kMaxDeviceLocks) + kMaxDeviceLocks) % kMaxDeviceLocks);
+    std::sort(devs.begin(), devs.end());
+    devs.erase(std::unique(devs.begin(), devs.end()), devs.end());
+    for (int d : devs) g_device_mu[d].lock();              // ascending order: no lock cycles
+    struct Unlock {
+        std::vector<int> &d;
+        ~Unlock() { for (auto it = d.rbegin(); it != d.rend(); ++it) g_device_mu[*it].unlock(); }
+    } unlock{devs};
     try {
         return iterate_locked(s, max_iters, out, trace_j, trace_r);
     } catch (const std::exception &ex) {
