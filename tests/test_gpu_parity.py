@@ -380,3 +380,43 @@ def test_degenerate_full_solve_final_basis_bit_exact(m, rule):
                                                              writeback_full=True))
     assert st == ost == _ffi.OK and res.iterations == oit
     assert np.array_equal(basis, o_basis) and np.array_equal(tab, o_tab)
+
+
+# ------------------------------------------------------------------ randomized shape sweep
+def _sweep_cases():
+    rng = np.random.default_rng(2024)
+    cases = []
+    for k in range(40):                                   # tiny to small, every alignment of C
+        cases.append((int(rng.integers(1, 70)), int(rng.integers(1, 90)), k))
+    cases += [(5, 10, 100), (15, 16, 101), (31, 32, 102)]            # C = n+m+1 multiple of 16: no pad
+    cases += [(3, 5000, 103), (1, 9000, 104), (2, 4200, 105),       # long rows, fewer rows than look CTAs
+              (700, 3500, 106), (1500, 40, 107), (4100, 3, 108)]    # multi-CTA look, tall and thin
+    return cases
+
+
+@pytest.mark.parametrize("m,n,seed", _sweep_cases())
+def test_random_shapes_signs_rules_bit_exact(m, n, seed):
+    """Mixed-sign data (optimal, unbounded and stalled outcomes all occur), max and min problems,
+    both pivot rules, every row-stride alignment; status, pivot trace, basis and every cell must
+    equal the oracle's."""
+    rng = np.random.default_rng(seed)
+    A = rng.random((m, n)) - (0.0 if seed % 3 else 0.3)
+    if seed % 4 == 0:
+        A = np.round(A * 4)                               # small integers: exact ties
+    b = rng.uniform(n / 8.0, 3.0 * n / 8.0, m) * (rng.random(m) > (0.2 if seed % 5 == 0 else -1))
+    c = rng.random(n) - (0.0 if seed % 2 else 0.2)
+    tab, basis = synthetic.tableau_from_lp(A, b, c)
+    is_max = seed % 7 != 0
+    rule = 1 if seed % 6 == 0 else 0
+    if not is_max:
+        tab[-1, :n] *= -1.0
+    cap = 3000
+    o_tab, o_basis = tab.copy(), basis.copy()
+    ost, oit, otrace = oracle.solve(o_tab, o_basis, is_max, rule=rule, max_iters=cap, trace_cap=cap,
+                                    parallel=m * n > 100000)
+    st, res, trace = _ffi.solve(tab, basis, is_max,
+                                _ffi.make_opts(pivot_rule=rule, max_iters=cap, trace_capacity=cap,
+                                               writeback_full=True))
+    assert (st, res.iterations) == (ost, oit)
+    assert trace == otrace
+    assert np.array_equal(basis, o_basis) and np.array_equal(tab, o_tab)
