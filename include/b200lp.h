@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200LP_VERSION 101 /* 0.1.1 */
+#define B200LP_VERSION 102 /* 0.1.2 */
 #define B200LP_MAX_DEVICES 8
 
 /* ---- status codes --------------------------------------------------------------------------
@@ -158,6 +158,11 @@ int b200lp_create_sharded(const b200lp_opts *opts, int64_t R, int64_t C, int32_t
 int b200lp_shard_rows(const b200lp_solver *s, int64_t *row_begin, int64_t *row_end);
 /* the partition rule itself (host arithmetic, no GPU): contiguous blocks of ceil(m/nranks) */
 void b200lp_partition(int64_t m, int32_t nranks, int32_t rank, int64_t *row_begin, int64_t *row_end);
+
+/* The one-shot calls keep up to four idle single-GPU handles (<= 64 MB of tableau each) so that
+ * runs of small solves -- branch and bound, test suites -- skip the ~3 ms of allocation per call.
+ * b200lp_shutdown() frees them; optional (they are also reclaimed at process exit). */
+void b200lp_shutdown(void);
 
 /* ---- misc ----------------------------------------------------------------------------------- */
 const char *b200lp_strerror(int code);

@@ -109,6 +109,7 @@ SIGNATURES = {
                                              ctypes.POINTER(_vp)]),
     "b200lp_shard_rows": (ctypes.c_int, [_vp, _lp, _lp]),
     "b200lp_partition": (None, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _lp, _lp]),
+    "b200lp_shutdown": (None, []),
     "b200lp_strerror": (ctypes.c_char_p, [ctypes.c_int]),
     "b200lp_version": (ctypes.c_int, []),
     "b200lp_device_count": (ctypes.c_int, []),
@@ -331,6 +332,11 @@ class DeviceTableau:
         _check(st, "b200lp_iterate")
         n = res.trace_len
         return st, res, list(zip(tj[:n].tolist(), tr[:n].tolist()))
+
+
+def shutdown():
+    """Free the idle handles pooled by the one-shot calls."""
+    lib().b200lp_shutdown()
 
 
 def comm_unique_id():

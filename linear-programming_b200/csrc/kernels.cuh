@@ -1,13 +1,19 @@
 // kernels.cuh -- sm_100a kernels of the dense tableau simplex iteration.
 //
-// One simplex iteration = the reference's loop body, src/simplex.lisp:455-460:
+// The solve loop (b200lp_iterate / b200lp_solve*) runs ONE kernel per iteration, k_iter
+// (second half of this file): lookahead CTAs + rank-1 update tiles, with the sharded candidate
+// exchange done inside the kernel over peer-mapped buffers; k_look + k_update are the same two
+// roles as separate kernels for the NCCL fallback.
+//
+// The step-by-step entry points (b200lp_find_entering_column, _find_pivoting_row, _pivot) map
+// one reference function (src/simplex.lisp) to one small kernel each (first half of this file):
 //   k_enter   find-entering-column  :362-379   reduced-cost row scan, (value,index) argmin
 //   k_ratio   find-pivoting-row     :382-389   strided column gather + ratio argmin; also
 //                                              snapshots the pivot column a[:,j] (n-pivot-row
 //                                              reads each a[r,j] before row r changes, :353)
 //   k_cand    n-pivot-row part 1    :344-348   candidate pivot row / pivot element
 //   k_winner  (sharded only)                   pick the global leaving row from all ranks
-//   k_pivot   n-pivot-row part 2    :349-358   rank-1 update, the HBM-bound hot kernel
+//   k_pivot   n-pivot-row part 2    :349-358   rank-1 update in place
 //
 // Arithmetic contract (bit-identical to the reference's double-float path and to
 // oracle/simplex_oracle.c): __ddiv_rn for the row scale and the ratios, __dmul_rn then

@@ -2,14 +2,17 @@
 // declared in include/b200lp.h.
 //
 // Replaces the reference's n-solve-tableau (src/simplex.lisp:399-461).  The tableau lives in
-// HBM for the whole solve; the host only enqueues iterations (every kernel returns at once when
-// the device status word says the solve is over) and polls that word every `poll_interval`
-// pivots, one batch behind the enqueue front so the GPU queue never drains.
+// HBM for the whole solve (two ping-pong buffers); the host only enqueues one k_iter launch per
+// iteration (every CTA returns at once when the ring slot says the solve is over) and polls a
+// Report word every `poll_interval` iterations, one batch behind the enqueue front so the GPU
+// queue never drains.  Launches use programmatic stream serialization (PDL).
 //
-// Sharding: contiguous row blocks (b200lp_partition), objective row replicated on every shard;
-// per iteration one NCCL all-gather carries each shard's (ratio, key, row | scaled candidate
-// row), after which every shard picks the same winner.  A shard is one GPU: either one per
-// process (b200lp_create_sharded, torchrun style) or several in this process (opts.ndev > 1).
+// Sharding: contiguous row blocks (b200lp_partition), objective row replicated on every shard.
+// The per-iteration exchange of candidate pivot rows happens inside k_iter through peer-mapped
+// buffers (setup_exchange: peer access in-process, CUDA IPC handles across processes); when
+// peers cannot be mapped, k_look / k_update run on two streams with an NCCL all-gather between
+// them.  A shard is one GPU: either one per process (b200lp_create_sharded, torchrun style) or
+// several in this process (opts.ndev > 1).
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -89,6 +92,9 @@ struct Shard {
     int m_local = 0;            // constraint rows owned
     int R_local = 0;            // m_local + 1 (objective replica last)
     int64_t ld = 0;             // device leading dimension (multiple of 16 doubles)
+    // allocation capacities (>= the current shape; a pooled handle is re-bound to other shapes)
+    int64_t cap_rows = 0, cap_ld = 0;
+    int cap_trace = 0;
     cudaStream_t stream = nullptr;      // uploads, step-by-step API, k_update
     cudaStream_t look_stream = nullptr; // k_look + candidate exchange (high priority)
     double *tabs[2] = {nullptr, nullptr}; // ping-pong tableau buffers; [1] allocated on first iterate
@@ -160,6 +166,39 @@ static void fill_thresholds(b200lp_solver *s)
     b200lp_thresholds(s->tol, &s->thr_enter, &s->thr_pivot, &s->thr_feas);
 }
 
+// Small single-GPU handles are pooled by the one-shot calls (create/destroy costs ~3 ms, a
+// tiny solve ~0.3 ms); their buffers are allocated with some slack so that nearby shapes --
+// branch-and-bound nodes add a row and a column per level -- reuse them.
+static constexpr double kPoolMaxBytes = 64e6;
+static bool poolable(const b200lp_solver *s, const Shard &sh)
+{
+    return s->world == 1 && 8.0 * (double)sh.ld * sh.R_local <= kPoolMaxBytes;
+}
+
+// Everything that depends only on the current shape (R_local, ld) of a shard.
+static void shape_shard(Shard &sh)
+{
+    // enough look CTAs that each thread touches only a few cells per scan; one CTA (no grid
+    // barriers) when the rows are short
+    sh.look_ctas = sh.ld <= 4096 ? 1 : (int)std::min<int64_t>(kLookMaxCtas, (sh.ld + 1023) / 1024);
+    sh.iter_ctas = 0;
+    sh.ratio_blocks = (sh.R_local + kRatioThreads - 1) / kRatioThreads;
+    sh.xchg.ld = sh.ld;
+}
+
+static int ensure_trace(b200lp_solver *s, Shard &sh)
+{
+    const int tc = s->opts.trace_capacity;
+    if (tc <= sh.cap_trace) return B200LP_OK;
+    cudaFree(sh.trace);
+    if (sh.h_trace) cudaFreeHost(sh.h_trace);
+    sh.trace = nullptr; sh.h_trace = nullptr; sh.cap_trace = 0;
+    CU_TRY(cudaMalloc(&sh.trace, sizeof(int2) * tc));
+    CU_TRY(cudaMallocHost(&sh.h_trace, sizeof(int2) * tc));
+    sh.cap_trace = tc;
+    return B200LP_OK;
+}
+
 static int alloc_shard(b200lp_solver *s, Shard &sh)
 {
     CU_TRY(cudaSetDevice(sh.device));
@@ -168,13 +207,19 @@ static int alloc_shard(b200lp_solver *s, Shard &sh)
     CU_TRY(cudaStreamCreateWithPriority(&sh.stream, cudaStreamNonBlocking, prio_lo));
     CU_TRY(cudaStreamCreateWithPriority(&sh.look_stream, cudaStreamNonBlocking, prio_hi));
     sh.ld = round_up(s->C, 16);
-    const int64_t stride = kCandHdr + sh.ld;
-    CU_TRY(cudaMalloc(&sh.tabs[0], sizeof(double) * sh.ld * sh.R_local));
+    sh.cap_rows = sh.R_local;
+    sh.cap_ld = sh.ld;
+    if (poolable(s, sh)) {                                 // room for nearby shapes (pool reuse)
+        sh.cap_rows = round_up(sh.R_local, 64);
+        sh.cap_ld = round_up(sh.ld, 256);
+    }
+    const int64_t stride = kCandHdr + sh.cap_ld;
+    CU_TRY(cudaMalloc(&sh.tabs[0], sizeof(double) * sh.cap_ld * sh.cap_rows));
     sh.cur = 0;
     sh.tab = sh.tabs[0];
-    CU_TRY(cudaMalloc(&sh.basis, sizeof(int32_t) * std::max(1, sh.m_local)));
-    CU_TRY(cudaMalloc(&sh.colout, sizeof(double) * sh.R_local));
-    CU_TRY(cudaMalloc(&sh.colring, sizeof(double) * sh.R_local * kRing));
+    CU_TRY(cudaMalloc(&sh.basis, sizeof(int32_t) * sh.cap_rows));
+    CU_TRY(cudaMalloc(&sh.colout, sizeof(double) * sh.cap_rows));
+    CU_TRY(cudaMalloc(&sh.colring, sizeof(double) * sh.cap_rows * kRing));
     CU_TRY(cudaMalloc(&sh.candring, sizeof(double) * stride * kRing));
     CU_TRY(cudaMemsetAsync(sh.candring, 0, sizeof(double) * stride * kRing, sh.stream));
     if (s->world > 1) {
@@ -191,25 +236,18 @@ static int alloc_shard(b200lp_solver *s, Shard &sh)
     CU_TRY(cudaMalloc(&sh.ring, kRing * sizeof(IterState)));
     CU_TRY(cudaMalloc(&sh.look_sync, sizeof(LookSync)));
     CU_TRY(cudaMemsetAsync(sh.look_sync, 0, sizeof(LookSync), sh.stream));
-    // enough look CTAs that each thread touches only a few cells per scan; one CTA (no grid
-    // barriers) when the rows are short
-    sh.look_ctas = sh.ld <= 4096 ? 1 : (int)std::min<int64_t>(kLookMaxCtas, (sh.ld + 1023) / 1024);
+    shape_shard(sh);
     CU_TRY(cudaMalloc(&sh.report, sizeof(Report)));
     CU_TRY(cudaMallocHost(&sh.h_report, 2 * sizeof(Report)));
     for (int k = 0; k < 4; ++k) {
         CU_TRY(cudaEventCreateWithFlags(&sh.ev_look[k], cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&sh.ev_upd[k], cudaEventDisableTiming));
     }
-    sh.ratio_blocks = (sh.R_local + kRatioThreads - 1) / kRatioThreads;
-    CU_TRY(cudaMalloc(&sh.partials, sizeof(Cand) * sh.ratio_blocks));
+    CU_TRY(cudaMalloc(&sh.partials, sizeof(Cand) * ((sh.cap_rows + kRatioThreads - 1) / kRatioThreads)));
     CU_TRY(cudaMalloc(&sh.st, sizeof(DevState)));
     CU_TRY(cudaMemsetAsync(sh.st, 0, sizeof(DevState), sh.stream));
     CU_TRY(cudaMallocHost(&sh.h_st, 2 * sizeof(DevState)));
-    const int tc = s->opts.trace_capacity;
-    if (tc > 0) {
-        CU_TRY(cudaMalloc(&sh.trace, sizeof(int2) * tc));
-        CU_TRY(cudaMallocHost(&sh.h_trace, sizeof(int2) * tc));
-    }
+    RC_TRY(ensure_trace(s, sh));
     CU_TRY(cudaEventCreate(&sh.ev_begin));
     CU_TRY(cudaEventCreate(&sh.ev_end));
     CU_TRY(cudaEventCreateWithFlags(&sh.ev_poll[0], cudaEventDisableTiming));
@@ -646,7 +684,7 @@ static int iterate_locked(b200lp_solver *s, int64_t limit, b200lp_result *out, i
     s->epoch += 1ull << 40;                                // fresh sequence numbers for this call
     for (Shard &sh : s->shards) {
         CU_TRY(cudaSetDevice(sh.device));
-        if (!sh.tabs[1]) CU_TRY(cudaMalloc(&sh.tabs[1], sizeof(double) * sh.ld * sh.R_local));
+        if (!sh.tabs[1]) CU_TRY(cudaMalloc(&sh.tabs[1], sizeof(double) * sh.cap_ld * sh.cap_rows));
         cudaStream_t st0 = fused ? sh.stream : sh.look_stream;
         IterState init;
         std::memset(&init, 0, sizeof(init));
@@ -816,7 +854,7 @@ static int upload_locked(b200lp_solver *s, const double *tab, int64_t ld, const 
             // of PCIe speed), staged in the spare ping-pong buffer, then re-pitched on the device
             const int other = sh.cur ^ 1;
             if (!sh.tabs[other])
-                CU_TRY(cudaMalloc(&sh.tabs[other], sizeof(double) * sh.ld * sh.R_local));
+                CU_TRY(cudaMalloc(&sh.tabs[other], sizeof(double) * sh.cap_ld * sh.cap_rows));
             double *stage = sh.tabs[other];
             if (sh.m_local > 0)
                 CU_TRY(cudaMemcpyAsync(stage, rows, wbytes * sh.m_local, cudaMemcpyHostToDevice, sh.stream));
@@ -1043,6 +1081,61 @@ static int ensure_nccl()
     return B200LP_OK;
 }
 
+// ---- handle pool of the one-shot calls ----------------------------------------------------------
+static std::mutex g_pool_mu;
+static std::vector<b200lp_solver *> g_pool;            // idle single-GPU handles
+static constexpr size_t kPoolSlots = 4;
+
+// Re-bind an idle pooled handle to a new problem shape and option set.
+static int rebind(b200lp_solver *s, const b200lp_opts *opts, int64_t R, int64_t C, int32_t is_max)
+{
+    if (opts) s->opts = *opts; else std::memset(&s->opts, 0, sizeof(s->opts));
+    s->R = R; s->C = C; s->m = R - 1; s->is_max = is_max ? 1 : 0;
+    fill_thresholds(s);
+    s->iters_done = 0;
+    Shard &sh = s->shards[0];
+    sh.row0 = 0; sh.m_local = (int)(R - 1); sh.R_local = (int)R;
+    sh.ld = round_up(C, 16);
+    shape_shard(sh);
+    CU_TRY(cudaSetDevice(sh.device));
+    return ensure_trace(s, sh);
+}
+
+// A handle for a one-shot solve on one GPU: from the pool when an idle one is large enough (and
+// not wastefully larger), else freshly created.
+static int acquire(const b200lp_opts *opts, int64_t R, int64_t C, int32_t is_max, b200lp_solver **out)
+{
+    const int nd = opts ? std::max(1, (int)opts->ndev) : 1;
+    const int device = opts ? opts->devices[0] : 0;
+    if (nd == 1 && R >= 2 && C >= 2) {
+        const int64_t ld = round_up(C, 16);
+        std::unique_lock<std::mutex> lk(g_pool_mu);
+        for (size_t k = 0; k < g_pool.size(); ++k) {
+            b200lp_solver *c = g_pool[k];
+            const Shard &sh = c->shards[0];
+            if (sh.device != device || R > sh.cap_rows || ld > sh.cap_ld) continue;
+            if (sh.cap_rows * sh.cap_ld > 4 * std::max<int64_t>(R * ld, 64 * 256)) continue;
+            g_pool.erase(g_pool.begin() + (long)k);
+            lk.unlock();
+            const int rc = rebind(c, opts, R, C, is_max);
+            if (rc != B200LP_OK) { b200lp_destroy(c); return rc; }
+            *out = c;
+            return B200LP_OK;
+        }
+    }
+    return b200lp_create(opts, R, C, is_max, out);
+}
+
+static void release(b200lp_solver *s)
+{
+    if (!s) return;
+    if (s->shards.size() == 1 && !s->multiprocess && poolable(s, s->shards[0])) {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (g_pool.size() < kPoolSlots) { g_pool.push_back(s); return; }
+    }
+    b200lp_destroy(s);
+}
+
 } // namespace b200lp
 
 // =============================================================================================
@@ -1069,6 +1162,16 @@ void b200lp_partition(int64_t m, int32_t nranks, int32_t rank, int64_t *row_begi
 }
 
 int b200lp_version(void) { return B200LP_VERSION; }
+
+void b200lp_shutdown(void)
+{
+    std::vector<b200lp_solver *> idle;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        idle.swap(g_pool);
+    }
+    for (b200lp_solver *s : idle) b200lp_destroy(s);
+}
 
 int b200lp_device_count(void)
 {
@@ -1309,7 +1412,7 @@ int b200lp_solve(const b200lp_opts *opts, double *tab, int64_t R, int64_t C, int
     if (!tab || !basis || ld < C) return fail(B200LP_ERR_INVALID_ARG, "solve", "null buffer or ld < C");
     const double t0 = now_ms();
     b200lp_solver *s = nullptr;
-    RC_TRY(b200lp_create(opts, R, C, is_max, &s));
+    RC_TRY(acquire(opts, R, C, is_max, &s));
     b200lp_result res;
     std::memset(&res, 0, sizeof(res));
     int rc = B200LP_OK;
@@ -1339,7 +1442,8 @@ int b200lp_solve(const b200lp_opts *opts, double *tab, int64_t R, int64_t C, int
             if (rc != B200LP_OK) status = rc;
         }
     }
-    b200lp_destroy(s);
+    if (status < 0) b200lp_destroy(s);                     // never pool a handle that saw an error
+    else release(s);
     res.status = status;
     res.ms_h2d = ms_h2d;
     res.h2d_bytes = (int64_t)sizeof(double) * R * C + (int64_t)sizeof(int32_t) * (R - 1);
@@ -1377,7 +1481,8 @@ int b200lp_solve_two_phase(const b200lp_opts *opts, double *art_tab, int64_t C_a
     auto finish = [&](int st) {
         if (art) { cudaSetDevice(art->shards[0].device); }
         cudaFree(d_is_basic); cudaFree(d_newcol); cudaFree(d_scales);
-        b200lp_destroy(art); b200lp_destroy(mn);
+        if (st < 0) { b200lp_destroy(art); b200lp_destroy(mn); }
+        else { release(art); release(mn); }
         if (out) {
             *out = r2;
             out->status = st;
@@ -1391,9 +1496,9 @@ int b200lp_solve_two_phase(const b200lp_opts *opts, double *art_tab, int64_t C_a
         return st;
     };
     const int64_t m = R - 1, nv = C - 1, art_nv = C_art - 1;
-    int rc = b200lp_create(opts, R, C_art, /*is_max=*/0, &art);   // phase 1 is a `min` problem
+    int rc = acquire(opts, R, C_art, /*is_max=*/0, &art);         // phase 1 is a `min` problem
     if (rc) return finish(rc);
-    rc = b200lp_create(opts, R, C, is_max, &mn);
+    rc = acquire(opts, R, C, is_max, &mn);
     if (rc) return finish(rc);
     if ((rc = b200lp_upload(art, art_tab, ld_art, art_basis))) return finish(rc);
     if ((rc = b200lp_upload(mn, main_tab, ld, main_basis))) return finish(rc);

@@ -420,3 +420,29 @@ def test_random_shapes_signs_rules_bit_exact(m, n, seed):
     assert (st, res.iterations) == (ost, oit)
     assert trace == otrace
     assert np.array_equal(basis, o_basis) and np.array_equal(tab, o_tab)
+
+
+def test_pooled_handles_are_rebound_cleanly_across_shapes():
+    """The one-shot calls reuse idle handles for nearby shapes; nothing of a previous solve (ring
+    slots, ping-pong parity, basis, trace, tolerances, rule) may leak into the next."""
+    shapes = [(30, 40), (31, 41), (12, 90), (33, 38), (2, 3), (60, 100), (30, 40), (64, 190), (5, 7)]
+    for k, (m, n) in enumerate(shapes * 2):
+        tab, basis = random_tableau(m, n, seed=500 + k, signed=k % 3 == 0)
+        rule, tol, cap = k % 2, (1024.0, 64.0)[k % 2], (0, 512, 4096)[k % 3]
+        o_tab, o_basis = tab.copy(), basis.copy()
+        ost, oit, otrace = oracle.solve(o_tab, o_basis, True, tol=tol, rule=rule, max_iters=2000,
+                                        trace_cap=cap)
+        st, res, trace = _ffi.solve(tab, basis, True,
+                                    _ffi.make_opts(fp_tolerance=tol, pivot_rule=rule, max_iters=2000,
+                                                   trace_capacity=cap, writeback_full=True))
+        assert (st, res.iterations) == (ost, oit) and trace == otrace[:cap]
+        assert np.array_equal(tab, o_tab) and np.array_equal(basis, o_basis)
+        if k == 9:
+            _ffi.shutdown()                                # dropping the pool is always safe
+    g = G.EQ_SOLVED                                        # two-phase draws two handles from the pool
+    b = g["initial"]
+    for _ in range(3):
+        art, ab = f64(b["art_matrix"]), i32(b["art_basis"])
+        main, mb = f64(b["main_matrix"]), i32(b["main_basis"])
+        st, res = _ffi.solve_two_phase(art, ab, main, mb, True, _ffi.make_opts(writeback_full=True))
+        assert st == _ffi.OK and mb.tolist() == g["main_basis"] and res.objective == 28.5
