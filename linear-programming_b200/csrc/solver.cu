@@ -712,13 +712,18 @@ static int iterate_locked(b200lp_solver *s, int64_t limit, b200lp_result *out, i
     int slot = 0;
     bool pending[2] = {false, false};
     long long k = 0;                                       // iterations enqueued
+    int batches = 0;
+    const bool opts_batch = s->opts.poll_interval > 0;     // an explicit interval is taken literally
     bool all_enqueued = false;
     for (;;) {
         if (!all_enqueued) {
             // With a cap, `limit` iterations decide everything: look(limit -> limit+1) tells
             // "optimal" from "iteration limit".  Without a cap keep the queue one poll ahead.
-            long long nb = batch;
-            if (limit > 0) nb = std::min<long long>(batch, limit - k);
+            // ramp 4, 8, 16, ... up to the poll interval: a solve of a few pivots should not
+            // pay for dozens of launches that find the solve already over
+            long long nb = opts_batch ? batch : std::min<long long>(batch, 4ll << std::min(batches, 8));
+            ++batches;
+            if (limit > 0) nb = std::min<long long>(nb, limit - k);
             for (long long b = 0; b < nb; ++b) {
                 ++k;
                 if (fused) {
