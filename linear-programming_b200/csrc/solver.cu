@@ -397,6 +397,24 @@ static int exchange(b200lp_solver *s, int slot = 0, bool on_look_stream = false)
 {
     if (s->world == 1) return B200LP_OK;
     const size_t bytes = sizeof(double) * (kCandHdr + s->shards[0].ld);
+    if (!s->multiprocess && !s->shards[0].comm) {
+        // several GPUs in this process and no NCCL communicator (peer-mapped mode): the
+        // step-by-step API gathers with peer copies, ordered by one event per source shard
+        for (Shard &a : s->shards) {
+            CU_TRY(cudaSetDevice(a.device));
+            const int64_t stride = kCandHdr + a.ld;
+            for (Shard &b : s->shards)
+                CU_TRY(cudaMemcpyPeerAsync(b.gathring + (slot * s->world + a.rank) * stride, b.device,
+                                           a.candring + slot * stride, a.device, bytes, a.stream));
+            CU_TRY(cudaEventRecord(a.ev_look[0], a.stream));
+        }
+        for (Shard &b : s->shards) {
+            CU_TRY(cudaSetDevice(b.device));
+            for (Shard &a : s->shards)
+                if (&a != &b) CU_TRY(cudaStreamWaitEvent(b.stream, a.ev_look[0], 0));
+        }
+        return B200LP_OK;
+    }
     if (s->shards.size() > 1) NCCL_TRY(g_nccl.GroupStart());
     for (Shard &sh : s->shards) {
         if (s->shards.size() > 1) cudaSetDevice(sh.device);
@@ -1231,7 +1249,10 @@ int b200lp_create(const b200lp_opts *opts, int64_t R, int64_t C, int32_t is_max,
         }
         int rc = B200LP_OK;
         for (Shard &sh : s->shards) { rc = alloc_shard(s, sh); if (rc) break; }
-        if (!rc && nd > 1) {
+        // Several GPUs in one process: peer access is all the in-kernel exchange needs; an NCCL
+        // communicator (seconds to create) is only built when peers cannot be mapped.
+        if (!rc) rc = setup_exchange(s);
+        if (!rc && nd > 1 && s->xmode == 1) {
             rc = ensure_nccl();
             if (!rc) {
                 std::vector<ncclComm_t> comms(nd);
@@ -1242,7 +1263,6 @@ int b200lp_create(const b200lp_opts *opts, int64_t R, int64_t C, int32_t is_max,
                 else for (int g = 0; g < nd; ++g) s->shards[g].comm = comms[g];
             }
         }
-        if (!rc) rc = setup_exchange(s);
         if (rc) { b200lp_destroy(s); *out = nullptr; return rc; }
         return B200LP_OK;
     } catch (const std::exception &ex) {

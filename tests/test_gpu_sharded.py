@@ -84,3 +84,28 @@ def test_two_phase_with_several_devices_requested_runs_on_the_first():
     main, mb = f64(b["main_matrix"]), np.array(b["main_basis"], np.int32)
     st, res = _ffi.solve_two_phase(art, ab, main, mb, True, _ffi.make_opts(devices=[0, 1]))
     assert st == _ffi.OK and res.objective == 28.5 and mb.tolist() == g["main_basis"]
+
+
+@needs2
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_step_by_step_api_on_a_multi_device_handle(exchange, monkeypatch):
+    """find-entering-column / find-pivoting-row / n-pivot-row one call at a time on a handle that
+    row-block shards over two GPUs of this process, against the oracle."""
+    monkeypatch.setenv("B200LP_EXCHANGE", exchange)
+    tab, basis = synthetic.dense_tableau(45, 70, seed=3)
+    o_tab, o_basis = tab.copy(), basis.copy()
+    with _ffi.DeviceTableau(*tab.shape, opts=_ffi.make_opts(devices=[0, 1])) as d:
+        d.upload(tab, basis)
+        for _ in range(12):
+            j = d.find_entering_column()
+            assert (j if j is not None else -1) == oracle.find_entering_column(o_tab, True)
+            if j is None:
+                break
+            r = d.find_pivoting_row(j)
+            assert (r if r is not None else -1) == oracle.find_pivoting_row(o_tab, o_basis, j)
+            d.pivot(j, r)
+            oracle.pivot(o_tab, o_basis, j, r)
+        st, res, _ = d.iterate(0)                          # and the pipelined loop picks up from there
+        oracle.solve(o_tab, o_basis, True)
+        g_tab, g_basis = d.download()
+    assert st == _ffi.OK and np.array_equal(g_tab, o_tab) and np.array_equal(g_basis, o_basis)
