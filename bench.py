@@ -221,7 +221,12 @@ def run_b200(args, cfg, workload):
             uid.copy_(torch.frombuffer(bytearray(_ffi.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
         shard = (rank, world, bytes(uid.cpu().numpy().tobytes()))
-    opts = _ffi.make_opts(devices=[local_rank], time_kernels=True, pivot_variant=args.variant,
+    # `--gpus N` without torchrun: one process drives N GPUs (the library shards in-process)
+    inproc = args.gpus if (world == 1 and args.gpus > 1) else 1
+    if inproc > torch.cuda.device_count():
+        raise SystemExit(f"bench.py: --gpus {inproc} but {torch.cuda.device_count()} visible")
+    devices = list(range(inproc)) if inproc > 1 else [local_rank]
+    opts = _ffi.make_opts(devices=devices, time_kernels=True, pivot_variant=args.variant,
                           poll_interval=args.poll)
     dev = _ffi.DeviceTableau(R, C, True, opts, shard=shard)
     if shard is None:
@@ -271,7 +276,7 @@ def run_b200(args, cfg, workload):
         t0 = time.perf_counter()
         if shard is None:
             eb = basis.copy()
-            st2, r2, _ = _ffi.solve(tab, eb, True, _ffi.make_opts(devices=[local_rank],
+            st2, r2, _ = _ffi.solve(tab, eb, True, _ffi.make_opts(devices=devices,
                                                                    pivot_variant=args.variant,
                                                                    poll_interval=args.poll,
                                                                    max_iters=args.e2e_max_iters))
@@ -297,7 +302,7 @@ def run_b200(args, cfg, workload):
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores --------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and inproc == 1 and not args.no_cpu_baseline:
         from oracle import oracle
         oracle.build()
         oracle.set_num_threads(len(os.sched_getaffinity(0)))
@@ -333,21 +338,22 @@ def run_b200(args, cfg, workload):
         peak, peak_src = load_peak()
         achieved = bytes_per_launch / (ms_pivot * 1e-3) / 1e9
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps_done,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world * inproc,
+            "steps": steps_done,
             "warmup": args.warmup, "ms_per_step": ms_total / max(steps_done, 1),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload, "m": m, "n": n, "R": R, "C": C,
-                       "tableau_bytes": 8 * R * C, "sharding": f"row-block x{world}",
+                       "tableau_bytes": 8 * R * C, "sharding": f"row-block x{world * inproc}" + (" (one process)" if inproc > 1 else ""),
                        "exchange": {0: "none (one shard)", 1: "NCCL all-gather between kernels",
                                     2: "peer-mapped buffers, inside the iteration kernel"}[
                                         int(res.exchange_mode)],
-                       "l2": "tableau >> 126 MB L2, no flush needed" if 8 * R * C // world > 3e8
+                       "l2": "tableau >> 126 MB L2, no flush needed" if 8 * R * C // (world * inproc) > 3e8
                              else "tableau per GPU may be L2 resident",
                        "status_after_steps": int(st)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
-                         "traffic": load_traffic(workload) if world == 1 else None,
+                         "traffic": load_traffic(workload) if world * inproc == 1 else None,
                          "kernel": "k_iter (rank-1 update tiles + lookahead CTAs)" if int(res.exchange_mode) != 1 else "k_update", "bytes_per_launch": bytes_per_launch,
                          "ms_per_launch": ms_pivot,
                          "ms_per_launch_isolated": ms_pivot_isolated,
