@@ -18,7 +18,7 @@
   (:import-from :linear-programming/simplex
                 #:build-tableau #:tableau-matrix #:tableau-basis-columns #:tableau-var-count
                 #:tableau-constraint-count #:tableau-instance-problem #:tableau-problem
-                #:tableau-variable #:tableau-objective-value #:tableau-fp-tolerance-factor)
+                #:tableau-variable #:tableau-objective-value)
   (:import-from :linear-programming/conditions
                 #:solver-error #:unbounded-problem-error #:infeasible-problem-error)
   (:export #:b200-solver #:install #:b200-error))
@@ -92,24 +92,28 @@
     tableau))
 
 (defun fill-opts (o tolerance devices pivot-rule max-iterations)
+  "Zero the b200lp_opts at O (every zero field = library default), then set what was asked for."
   (dotimes (k (cffi:foreign-type-size '(:struct opts)))
     (setf (cffi:mem-aref o :uint8 k) 0))
-  (cffi:with-foreign-slots ((fp-tolerance-factor (pr pivot-rule) max-iters ndev) o (:struct opts))
-    (setf fp-tolerance-factor (coerce tolerance 'double-float)
-          pr (or pivot-rule 0)
-          max-iters (or max-iterations 0)
-          ndev (if (> (length devices) 1) (length devices) 0)))
-  (loop for d in devices for k from 0
-        do (setf (cffi:mem-aref (cffi:foreign-slot-pointer o '(:struct opts) 'devices) :int32 k) d)))
+  (flet ((slot (name value)
+           (setf (cffi:foreign-slot-value o '(:struct opts) name) value)))
+    (slot 'fp-tolerance-factor (coerce tolerance 'double-float))
+    (slot 'pivot-rule (or pivot-rule 0))
+    (slot 'max-iters (or max-iterations 0))
+    (slot 'ndev (if (> (length devices) 1) (length devices) 0)))
+  (let ((dev (cffi:foreign-slot-pointer o '(:struct opts) 'devices)))
+    (loop for d in devices
+          for k from 0 below 8
+          do (setf (cffi:mem-aref dev :int32 k) d))))
 
-(defun gpu-solve-tableau (tableau &key devices pivot-rule max-iterations)
+(defun gpu-solve-tableau (tableau &key (tolerance 1024) devices pivot-rule max-iterations)
   "n-solve-tableau (src/simplex.lisp:399-461) on the GPU.  TABLEAU is a tableau or the
 (art main) list build-tableau returns; the (main) tableau is returned, solved."
   (let* ((two-phase (listp tableau))
          (main (if two-phase (second tableau) tableau))
          (is-max (if (eq 'max (problem-type (tableau-instance-problem main))) 1 0)))
     (cffi:with-foreign-objects ((o '(:struct opts)) (res '(:struct result)))
-      (fill-opts o (tableau-fp-tolerance-factor main) devices pivot-rule max-iterations)
+      (fill-opts o tolerance devices pivot-rule max-iterations)
       (multiple-value-bind (tab basis rows cols) (export-tableau main)
         (unwind-protect
              (progn
@@ -161,7 +165,8 @@ with the library's own fp= tolerance (src/utils.lisp:84-93)."
   "The *solver* backend function.  Keywords: :fp-tolerance (as simplex-solver, src/simplex.lisp:511),
 :devices (list of CUDA ordinals; more than one row-block shards the tableau), :pivot-rule
 (0 reference rule, 1 Bland), :max-iterations."
-  (let ((backend-args (list :devices devices :pivot-rule pivot-rule :max-iterations max-iterations))
+  (let ((backend-args (list :tolerance fp-tolerance :devices devices :pivot-rule pivot-rule
+                            :max-iterations max-iterations))
         (better (if (eq (problem-type problem) 'max) #'< #'>))
         (best nil) (solution nil) (stack (list '())))
     (loop while stack
