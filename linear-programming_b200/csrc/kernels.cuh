@@ -375,6 +375,8 @@ constexpr int ST_PEER_TIMEOUT = -7;      // == B200LP_ERR_PEER_TIMEOUT
 constexpr int kRing = 4;
 constexpr int kLookThreads = 256;        // == kPivotThreads: both roles share k_iter's CTA shape
 constexpr int kLookMaxCtas = 32;
+constexpr int kLookBatch = 16;           // row cells a look thread loads before using the first
+constexpr int kLookRows = 8;             // tableau rows a look thread gathers per batch
 constexpr int kMaxWorld = 8;
 
 struct alignas(16) IterState {
@@ -598,15 +600,28 @@ __device__ __forceinline__ void look_role(const LookArgs &A, const int cta, cons
         const int c_end = min(nv, (cta + 1) * chunk);
         Cand best;
         best.q = 0.0; best.key = 0; best.row = -1;
-#pragma unroll 4
-        for (int cc = cta * chunk + tid; cc < c_end; cc += kLookThreads) {
-            double v = obj[cc];
-            if (pending) v = __dsub_rn(v, __dmul_rn(t_obj, prow[cc]));
-            const double k = A.is_max ? v : -v;
-            if (A.rule == 0) {
-                if (best.row < 0 || k < best.q) { best.q = k; best.key = cc; best.row = cc; }
-            } else if (best.row < 0 && k < 0.0 - A.thr_enter) {
-                best.q = 0.0; best.key = cc; best.row = cc;   // Bland: lowest passing index
+        // kLookBatch loads of a thread are in flight together: the scan costs one memory round
+        // trip per batch instead of one per element (this chain is pure latency)
+        for (int base = cta * chunk + tid; base < c_end; base += kLookBatch * kLookThreads) {
+            double vo[kLookBatch], vp[kLookBatch];
+#pragma unroll
+            for (int u = 0; u < kLookBatch; ++u) {
+                const int cc = base + u * kLookThreads;
+                vo[u] = cc < c_end ? obj[cc] : 0.0;
+                vp[u] = (pending && cc < c_end) ? prow[cc] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < kLookBatch; ++u) {
+                const int cc = base + u * kLookThreads;
+                if (cc >= c_end) break;
+                double v = vo[u];
+                if (pending) v = __dsub_rn(v, __dmul_rn(t_obj, vp[u]));
+                const double k = A.is_max ? v : -v;
+                if (A.rule == 0) {
+                    if (best.row < 0 || k < best.q) { best.q = k; best.key = cc; best.row = cc; }
+                } else if (best.row < 0 && k < 0.0 - A.thr_enter) {
+                    best.q = 0.0; best.key = cc; best.row = cc;   // Bland: lowest passing index
+                }
             }
         }
         best = cand_block_min<kLookThreads>(best, red);
@@ -628,23 +643,35 @@ __device__ __forceinline__ void look_role(const LookArgs &A, const int cta, cons
         const double pb = pending ? prow[rhs] : 0.0;
         const int chunk = (A.R_local + G - 1) / G;
         const int r_end = min(A.R_local, (cta + 1) * chunk);
-#pragma unroll 2
-        for (int i = cta * chunk + tid; i < r_end; i += kLookThreads) {
-            const double *rowp = A.src + (int64_t)i * A.ld;
-            double a = rowp[j];
-            double b = rowp[rhs];
-            if (pending) {
-                const double t = col[i];
-                a = (i == p_local) ? pj : __dsub_rn(a, __dmul_rn(t, pj));
-                b = (i == p_local) ? pb : __dsub_rn(b, __dmul_rn(t, pb));
+        for (int base = cta * chunk + tid; base < r_end; base += kLookRows * kLookThreads) {
+            double va[kLookRows], vb[kLookRows], vt[kLookRows];
+#pragma unroll
+            for (int u = 0; u < kLookRows; ++u) {
+                const int i = base + u * kLookThreads;
+                const bool in = i < r_end;
+                const double *rowp = A.src + (int64_t)(in ? i : 0) * A.ld;
+                va[u] = in ? rowp[j] : 0.0;
+                vb[u] = in ? rowp[rhs] : 0.0;
+                vt[u] = (pending && in) ? col[i] : 0.0;
             }
-            col_out[i] = a;
-            if (i < A.m_local && 0.0 + A.thr_pivot < a) {
-                Cand d;
-                d.q = __ddiv_rn(b, a);
-                d.key = A.rule ? ((i == p_local) ? st.j : A.basis[i]) : A.row0 + i;
-                d.row = A.row0 + i;
-                c = cand_min(c, d);
+#pragma unroll
+            for (int u = 0; u < kLookRows; ++u) {
+                const int i = base + u * kLookThreads;
+                if (i >= r_end) break;
+                double a = va[u], b = vb[u];
+                if (pending) {
+                    const double t = vt[u];
+                    a = (i == p_local) ? pj : __dsub_rn(a, __dmul_rn(t, pj));
+                    b = (i == p_local) ? pb : __dsub_rn(b, __dmul_rn(t, pb));
+                }
+                col_out[i] = a;
+                if (i < A.m_local && 0.0 + A.thr_pivot < a) {
+                    Cand d;
+                    d.q = __ddiv_rn(b, a);
+                    d.key = A.rule ? ((i == p_local) ? st.j : A.basis[i]) : A.row0 + i;
+                    d.row = A.row0 + i;
+                    c = cand_min(c, d);
+                }
             }
         }
         __syncthreads();                                       // red[] reuse
@@ -705,19 +732,31 @@ __device__ __forceinline__ void look_role(const LookArgs &A, const int cta, cons
             const int ld = (int)A.ld;
             const int chunk3 = (ld + G - 1) / G;
             const int e3 = min(ld, (cta + 1) * chunk3);
-#pragma unroll 4
-            for (int cc = cta * chunk3 + tid; cc < e3; cc += kLookThreads) {
-                double v = 0.0;
-                if (cc < A.C) {
-                    v = rowp[cc];
-                    if (pending) v = is_p ? prow[cc] : __dsub_rn(v, __dmul_rn(t, prow[cc]));
-                    v = __ddiv_rn(v, s);
+            for (int base = cta * chunk3 + tid; base < e3; base += kLookBatch * kLookThreads) {
+                double vr[kLookBatch], vp[kLookBatch];
+#pragma unroll
+                for (int u = 0; u < kLookBatch; ++u) {
+                    const int cc = base + u * kLookThreads;
+                    const bool in = cc < e3 && cc < A.C;
+                    vr[u] = (in && !(pending && is_p)) ? rowp[cc] : 0.0;
+                    vp[u] = (in && pending) ? prow[cc] : 0.0;
                 }
-                if (A.mode == 2) {
-                    const int64_t off = xchg_row_off(A.slot_out, A.ld) + cc;
-                    for (int g = 0; g < A.world; ++g) A.xchg.peer[g][off] = v;
-                } else {
-                    cand_out[kCandHdr + cc] = v;
+#pragma unroll
+                for (int u = 0; u < kLookBatch; ++u) {
+                    const int cc = base + u * kLookThreads;
+                    if (cc >= e3) break;
+                    double v = 0.0;
+                    if (cc < A.C) {
+                        v = vr[u];
+                        if (pending) v = is_p ? vp[u] : __dsub_rn(v, __dmul_rn(t, vp[u]));
+                        v = __ddiv_rn(v, s);
+                    }
+                    if (A.mode == 2) {
+                        const int64_t off = xchg_row_off(A.slot_out, A.ld) + cc;
+                        for (int g = 0; g < A.world; ++g) A.xchg.peer[g][off] = v;
+                    } else {
+                        cand_out[kCandHdr + cc] = v;
+                    }
                 }
             }
             if (A.mode == 2) __threadfence_system();
@@ -883,7 +922,7 @@ __global__ void __launch_bounds__(kLookThreads) k_look(const LookArgs A)
 // tile t (row-block major, so consecutive CTAs cover one 64-row slab left to right).  The block
 // scheduler dispatches in index order, so the look CTAs are resident before any tile.
 template <int TR, int UNROLL, bool STREAM>
-__global__ void __launch_bounds__(kPivotThreads, UNROLL >= 16 ? 2 : 4)
+__global__ void __launch_bounds__(kPivotThreads, 2)
 k_iter(const LookArgs A, const UpdateArgs U, const int look_ctas)
 {
     // Programmatic dependent launch: this grid may be made resident while the previous
