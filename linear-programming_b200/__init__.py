@@ -10,6 +10,7 @@ simplex.py    tableau struct, build_tableau, accessors, branch and bound (src/si
               the hot path, which only exists on the GPU)
 problem.py / expressions.py / sexp.py / conditions.py   the DSL front end feeding build_tableau
 external_formats.py   read_sexp / write_sexp / read_mps / write_standard_format
+utils.py      bound helpers and the fp=/fp</fp> tolerance predicates the device thresholds restate
 sharded.py    one-process-per-GPU row-block sharding (host plumbing)
 synthetic.py  BASELINE.json's synthetic dense LPs
 """

@@ -8,6 +8,7 @@ from .conditions import InvalidBoundsError, ParsingError
 from .expressions import (CONSTANT, parse_linear_expression, scale_linear_expression,
                           sum_linear_expressions)
 from .sexp import as_form
+from .utils import lb_max as _lb_max, ub_min as _ub_min, validate_bounds
 
 _gensym = itertools.count()
 
@@ -29,13 +30,6 @@ class Problem:
     var_bounds: list = field(default_factory=list)
     constraints: list = field(default_factory=list)
 
-
-def _lb_max(x, y):
-    return y if x is None else x if y is None else max(x, y)        # src/utils.lisp:44-50
-
-
-def _ub_min(x, y):
-    return y if x is None else x if y is None else min(x, y)        # src/utils.lisp:52-58
 
 
 def _add_bound(table, var, new, implicit_lb=None):
@@ -107,8 +101,7 @@ def parse_linear_constraints(exprs):
             else:
                 simple.append((">=", [(v, -c) for v, c in terms], -const))
     for var, (lb, ub) in bounds.items():                           # validate-bounds, utils.lisp:69-76
-        if lb is not None and ub is not None and ub < lb:
-            raise InvalidBoundsError(var, ub, lb)
+        validate_bounds(lb, ub, var)
     return simple, integer, [(var, b) for var, b in bounds.items()]
 
 

@@ -21,9 +21,7 @@ from . import _ffi
 from .conditions import (InfeasibleProblemError, ParsingError, SolverError,
                          UnboundedProblemError, raise_for_status)
 from .problem import Problem
-
-# CL double-float-epsilon as SBCL defines it (src/utils.lisp:92,107 scale it by the factor)
-CL_DOUBLE_FLOAT_EPSILON = float.fromhex("0x1.0000000000001p-53")
+from .utils import DOUBLE_FLOAT_EPSILON as CL_DOUBLE_FLOAT_EPSILON
 
 
 @dataclass
