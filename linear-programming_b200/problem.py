@@ -4,7 +4,7 @@ import itertools
 import warnings
 from dataclasses import dataclass, field
 
-from .conditions import InvalidBoundsError, ParsingError
+from .conditions import ParsingError
 from .expressions import (CONSTANT, parse_linear_expression, scale_linear_expression,
                           sum_linear_expressions)
 from .sexp import as_form
