@@ -1,0 +1,85 @@
+"""Random small LPs in the DSL (mixed <=, >=, = rows, every kind of variable bound, max and min),
+with scipy's HiGHS as an independent judge of the outcome.  Shared by the CPU test (oracle standing
+in for the device) and the GPU test (real backend)."""
+import numpy as np
+from scipy.optimize import linprog
+
+from linear_programming_b200 import conditions, problem as P, solver
+
+
+def generate(seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(2, 7))
+    m = int(rng.integers(1, 7))
+    names = [f"v{i}" for i in range(n)]
+    sense = "max" if rng.random() < 0.5 else "min"
+    c = rng.integers(-5, 6, size=n)
+    forms, A_ub, b_ub, A_eq, b_eq = [], [], [], [], []
+    for _ in range(m):
+        a = rng.integers(-4, 6, size=n) * (rng.random(n) < 0.8)
+        if np.count_nonzero(a) < 2:                       # single-variable rows become bounds: keep them apart
+            a[:2] = (1, 1)
+        rhs = int(rng.integers(-6, 25))
+        op = ("<=", ">=", "=")[int(rng.choice(3, p=[0.6, 0.25, 0.15]))]
+        lhs = "(+ " + " ".join(f"(* {int(k)} {v})" for k, v in zip(a, names) if k != 0) + ")"
+        forms.append(f"({op} {lhs} {rhs})")
+        if op == "<=":
+            A_ub.append(a); b_ub.append(rhs)
+        elif op == ">=":
+            A_ub.append(-a); b_ub.append(-rhs)
+        else:
+            A_eq.append(a); b_eq.append(rhs)
+    bounds, entries = [], []
+    for v in names:
+        kind = int(rng.integers(0, 6))
+        lo, hi = 0, None                                   # implicit x >= 0
+        if kind == 1:
+            lo = int(rng.integers(-3, 4)); entries.append(f"({lo} {v})")
+        elif kind == 2:
+            lo, hi = None, int(rng.integers(0, 9)); entries.append(f"({v} {hi})")
+        elif kind == 3:
+            # hi >= 0 only: for a NEGATIVE upper bound next to a lower bound the reference's
+            # build-tableau emits `var >= -ub` (src/simplex.lisp:199-203), a quirk the backend
+            # reproduces faithfully and HiGHS naturally does not
+            lo = int(rng.integers(-3, 3)); hi = max(0, lo + int(rng.integers(0, 8))); entries.append(f"({lo} {v} {hi})")
+        elif kind == 4:
+            lo, hi = None, None; entries.append(f"({v})")
+        bounds.append((lo, hi))
+    if entries:
+        forms.append("(bounds " + " ".join(entries) + ")")
+    objective = f"({sense} (+ " + " ".join(f"(* {int(k)} {v})" for k, v in zip(c, names)) + "))"
+    sign = -1.0 if sense == "max" else 1.0
+    kw = dict(A_ub=np.array(A_ub) if A_ub else None, b_ub=b_ub or None,
+              A_eq=np.array(A_eq) if A_eq else None, b_eq=b_eq or None, bounds=bounds, method="highs")
+    ref = linprog(sign * c, **kw)
+    # HiGHS' presolve reports some unbounded problems as "infeasible" (dual infeasibility);
+    # a zero-objective solve settles whether a feasible point exists
+    ref.feasible = ref.status == 0 or linprog(np.zeros(n), **kw).status == 0
+    return objective, forms, names, sign, ref
+
+
+def check(seed):
+    """Returns a short verdict string; raises AssertionError on a disagreement with HiGHS."""
+    objective, forms, names, sign, ref = generate(seed)
+    problem = P.make_linear_problem(objective, *forms)
+    try:
+        sol = solver.solve_problem(problem)
+    except conditions.InfeasibleProblemError:
+        assert not ref.feasible, (seed, "backend: infeasible", ref.status, ref.message)
+        return "infeasible"
+    except conditions.UnboundedProblemError:
+        assert ref.feasible and ref.status != 0, (seed, "backend: unbounded", ref.status, ref.message)
+        return "unbounded"
+    except conditions.SolverError as exc:                  # the reference's plain `error` on a stuck artificial
+        if "Artificial" in str(exc):
+            return "stuck"
+        raise
+    assert ref.status == 0, (seed, "backend: optimal", ref.status, ref.message)
+    want = sign * ref.fun
+    got = solver.solution_objective_value(sol)
+    assert abs(got - want) <= 1e-7 * max(1.0, abs(want)), (seed, got, want)
+    x = np.array([solver.solution_variable(sol, v) if v in problem.vars else 0.0 for v in names])
+    # the reported point must itself be feasible for HiGHS's statement of the problem
+    coefs = dict(problem.objective_func)
+    assert abs(sum(coefs.get(v, 0) * xi for v, xi in zip(names, x)) - got) <= 1e-7 * max(1.0, abs(got))
+    return "optimal"

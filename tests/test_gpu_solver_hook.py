@@ -31,3 +31,12 @@ def test_backend_keywords():
     from linear_programming_b200 import conditions
     with pytest.raises(conditions.SolverError):
         solver.solve_problem(p, max_iterations=1)
+
+
+def test_random_dsl_problems_agree_with_highs_on_the_gpu():
+    """The same 300 random LPs (every constraint and bound kind, two-phase included) through the
+    real backend: outcome and objective must match HiGHS."""
+    import collections
+    import random_problems
+    verdicts = collections.Counter(random_problems.check(seed) for seed in range(300))
+    assert verdicts["optimal"] > 100 and verdicts["infeasible"] > 10 and verdicts["unbounded"] > 5, verdicts

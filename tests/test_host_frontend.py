@@ -206,3 +206,13 @@ def test_status_codes_map_onto_the_reference_conditions():
             conditions.raise_for_status(code)
     assert issubclass(conditions.InfeasibleIntegerConstraintsError, conditions.InfeasibleProblemError)
     assert issubclass(conditions.UnboundedProblemError, conditions.SolverError)
+
+
+def test_random_dsl_problems_agree_with_highs(oracle_device):
+    """parse -> build-tableau (bounds, negated rows, artificials) -> solve -> accessors, against an
+    independent solver, on 300 random small LPs; the oracle stands in for the device."""
+    import collections
+    import random_problems
+    verdicts = collections.Counter(random_problems.check(seed) for seed in range(300))
+    assert verdicts["optimal"] > 100 and verdicts["infeasible"] > 10 and verdicts["unbounded"] > 5, verdicts
+    assert verdicts["stuck"] <= 3, verdicts
