@@ -138,6 +138,8 @@ def build_tableau(problem, instance_problem, fp_tolerance_factor=1024):
         if bound is None:
             mappings[var] = ("positive", column, 0)
         elif lb is not None and ub is not None:
+            # kept exactly as the reference writes it (:199-203), including `var >= -ub` for a
+            # negative upper bound -- see DESIGN.md section 2
             constraints.insert(0, ("<=", [(var, 1)], ub) if 0 <= ub else (">=", [(var, 1)], -ub))
             mappings[var] = ("positive", column, lb)
         elif lb is not None:
