@@ -83,3 +83,34 @@ def check(seed):
     coefs = dict(problem.objective_func)
     assert abs(sum(coefs.get(v, 0) * xi for v, xi in zip(names, x)) - got) <= 1e-7 * max(1.0, abs(got))
     return "optimal"
+
+
+def check_integer(seed):
+    """A random small pure-integer LP through the hook's branch and bound, against scipy's MILP."""
+    from scipy.optimize import Bounds, LinearConstraint, milp
+    rng = np.random.default_rng(10_000 + seed)
+    n = int(rng.integers(2, 5))
+    m = int(rng.integers(2, 5))
+    names = [f"k{i}" for i in range(n)]
+    sense = "max" if rng.random() < 0.7 else "min"
+    c = rng.integers(1, 9, size=n) * (1 if sense == "max" else -1) * rng.choice([1, 1, 1, -1], size=n)
+    A = rng.integers(0, 7, size=(m, n))
+    A[:, 0] = np.maximum(A[:, 0], 1)
+    A[0] = np.maximum(A[0], 1)                              # every variable is capped by row 0
+    b = rng.integers(5, 40, size=m)
+    forms = ["(<= (+ " + " ".join(f"(* {int(k)} {v})" for k, v in zip(row, names) if k) + f") {int(r)})"
+             for row, r in zip(A, b)]
+    forms.append("(integer " + " ".join(names) + ")")
+    objective = f"({sense} (+ " + " ".join(f"(* {int(k)} {v})" for k, v in zip(c, names)) + "))"
+    sign = -1.0 if sense == "max" else 1.0
+    ref = milp(sign * c, constraints=LinearConstraint(A, ub=b), integrality=np.ones(n),
+               bounds=Bounds(0, np.inf))
+    problem = P.make_linear_problem(objective, *forms)
+    sol = solver.solve_problem(problem)
+    assert ref.status == 0, (seed, ref.message)
+    got, want = solver.solution_objective_value(sol), sign * ref.fun
+    assert abs(got - want) <= 1e-7 * max(1.0, abs(want)), (seed, got, want)
+    x = [solver.solution_variable(sol, v) for v in names]
+    assert all(abs(xi - round(xi)) < 1e-9 for xi in x), (seed, x)
+    assert (A @ np.round(x) <= b + 1e-9).all(), (seed, x)
+    return got

@@ -40,3 +40,10 @@ def test_random_dsl_problems_agree_with_highs_on_the_gpu():
     import random_problems
     verdicts = collections.Counter(random_problems.check(seed) for seed in range(300))
     assert verdicts["optimal"] > 100 and verdicts["infeasible"] > 10 and verdicts["unbounded"] > 5, verdicts
+
+
+def test_random_integer_problems_on_the_gpu():
+    """Branch and bound with every node's relaxation solved on the B200 (pooled handles)."""
+    import random_problems
+    for seed in range(40):
+        random_problems.check_integer(seed)

@@ -216,3 +216,10 @@ def test_random_dsl_problems_agree_with_highs(oracle_device):
     verdicts = collections.Counter(random_problems.check(seed) for seed in range(300))
     assert verdicts["optimal"] > 100 and verdicts["infeasible"] > 10 and verdicts["unbounded"] > 5, verdicts
     assert verdicts["stuck"] <= 3, verdicts
+
+
+def test_random_integer_problems_agree_with_a_milp_solver(oracle_device):
+    """Branch and bound (src/simplex.lisp:466-542 as b200_solver) on 80 random pure-integer LPs."""
+    import random_problems
+    for seed in range(80):
+        random_problems.check_integer(seed)
