@@ -155,7 +155,7 @@ struct b200lp_solver {
     // 2 peer-mapped buffers written by the look role inside k_iter
     int xmode = 0;
     unsigned long long epoch = 0;
-    unsigned long long peer_timeout_ns = 20ull * 1000 * 1000 * 1000;
+    unsigned long long peer_timeout_ns = 120ull * 1000 * 1000 * 1000;   // B200LP_PEER_TIMEOUT_MS
 };
 
 namespace b200lp {
