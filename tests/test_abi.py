@@ -108,3 +108,28 @@ def test_argument_validation_happens_before_any_device_work():
         _ffi.solve(np.zeros((3, 6)), np.zeros(5, np.int32))
     with pytest.raises(ValueError):
         _ffi.make_opts(devices=list(range(9)))
+
+
+def _build_c_consumer(tmp_path):
+    exe = tmp_path / "c_abi_consumer"
+    libdir = os.path.dirname(_ffi.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_abi_consumer.c"), "-o", str(exe),
+                           "-L", libdir, "-l:libb200lp.so", f"-Wl,-rpath,{libdir}"])
+    return exe
+
+
+def test_plain_c_consumer_links_and_is_refused_without_a_gpu(tmp_path):
+    """include/b200lp.h is valid C99 and the library links from C with no torch / Python around."""
+    exe = _build_c_consumer(tmp_path)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    if _ffi.device_count() == 0:
+        assert "no device" in out.stdout
+
+
+@pytest.mark.gpu
+def test_plain_c_consumer_solves_on_the_gpu(tmp_path):
+    exe = _build_c_consumer(tmp_path)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "solved: objective 28.5 in 2 pivots" in out.stdout, out.stdout + out.stderr
