@@ -90,6 +90,15 @@ typedef struct b200lp_result {
     double  ms_look_kernel;      /* sum of lookahead-kernel durations (time_kernels only)           */
     double  ms_exchange;         /* sum of candidate-exchange durations (time_kernels, sharded)     */
     int64_t look_kernel_launches;
+    /* how the loop ran and where the decision chain spent its time (persistent loop, summed over
+     * pivots, %globaltimer on look CTA 0) */
+    int32_t loop_mode;           /* 1 = one k_iter launch per pivot, 2 = one persistent cooperative kernel */
+    int32_t look_ctas;
+    double  ms_look_wait;        /* waiting for the tile CTAs to finish update(k-2)                 */
+    double  ms_look_ratio;       /* phase A: pivot-column gather + ratio test                       */
+    double  ms_look_push;        /* sharded: scale own candidate row + push to every rank           */
+    double  ms_look_peer_wait;   /* sharded: waiting for every rank's candidate                     */
+    double  ms_look_row;         /* phase B: pivot row / element, objective row, next entering col  */
 } b200lp_result;
 
 /* ---- one-shot calls: what the `*solver*` backend function uses ------------------------------

@@ -72,6 +72,13 @@ class Result(ctypes.Structure):
         ("ms_look_kernel", ctypes.c_double),
         ("ms_exchange", ctypes.c_double),
         ("look_kernel_launches", ctypes.c_int64),
+        ("loop_mode", ctypes.c_int32),
+        ("look_ctas", ctypes.c_int32),
+        ("ms_look_wait", ctypes.c_double),
+        ("ms_look_ratio", ctypes.c_double),
+        ("ms_look_push", ctypes.c_double),
+        ("ms_look_peer_wait", ctypes.c_double),
+        ("ms_look_row", ctypes.c_double),
     ]
 
     def as_dict(self):

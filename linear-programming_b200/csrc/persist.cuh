@@ -1,0 +1,607 @@
+// persist.cuh -- the whole simplex loop (src/simplex.lisp:455-460) as ONE cooperative kernel.
+//
+// k_iter (kernels.cuh) launches one grid per pivot; on a 1 025-row shard (config 3 on 8 GPUs) or
+// an L2-resident tableau (config 2) the launch gap, the drain of the last wave of tiles and the
+// grid barriers of the decision chain are a visible share of a 15-60 us iteration.  k_persist
+// keeps one grid resident for the whole b200lp_iterate call (cudaLaunchCooperativeKernel: the
+// co-residency the spin waits need is guaranteed by the launch, not by dispatch order):
+//
+//   look CTAs  [0, G)   decide pivot k = (entering column, leaving row, scaled pivot row) while
+//                       the tile CTAs are still applying pivot k-1 -- the same lookahead algebra
+//                       as k_iter (every cell of S_{k-1} the decision needs is recomputed from
+//                       S_{k-2} and pivot k-1 with the update's own rounded product and rounded
+//                       difference).  They keep COMPACT running copies of the objective row and
+//                       of the RHS column (bit-identical to the tableau's, L2 resident), so only
+//                       the pivot column gather and the pivot row read touch the streamed tableau.
+//                       Two phases per pivot:  A  ratio test on column j_k (find-pivoting-row,
+//                       :382-389) + pivot-column snapshot;  B  pivot row / pivot element
+//                       (n-pivot-row part 1, :344-348) fused with the objective-row update and
+//                       the argmin that picks j_{k+1} (find-entering-column, :362-379).
+//   tile CTAs  [G, P)   n-pivot-row part 2 (:349-358): each owns a FIXED, balanced (to one row
+//                       of 512 columns) share of the tableau for the whole call and streams it
+//                       S_{k-1} -> S_k between the two ping-pong buffers as soon as decision k
+//                       is published.  A thread only ever re-reads cells it wrote itself, so the
+//                       tile role needs no grid barrier at all; CTAs drift up to an iteration
+//                       apart and there is no tail.
+//
+// Flow control (PSync, global memory): `decided` = highest published decision; done[k&3] counts
+// the tile CTAs that finished update(k).  Decision k needs update(k-2) complete (it reads
+// S_{k-2}); update(k) needs decision k.  Every spin has a %globaltimer timeout that aborts the
+// whole grid (-> B200LP_ERR_INTERNAL / B200LP_ERR_PEER_TIMEOUT) instead of hanging.
+//
+// Sharded (exchange mode 2, peer-mapped buffers over NVLink): after phase A every rank scales ITS
+// OWN candidate row speculatively and pushes header + row to every rank with 16-byte stores, then
+// raises one flag per destination; each rank waits for all flags ONCE, picks the same
+// lexicographic (ratio, key) minimum and runs the objective-row half of phase B on the winner's
+// row.  One flag wait per pivot (k_iter needs two: headers, then the winner's row).
+//
+// Arithmetic contract as everywhere: __ddiv_rn, __dmul_rn then __dsub_rn, strict compares,
+// lowest index wins.  Bit-identical to k_iter, to the step-by-step kernels and to the oracle.
+#pragma once
+#include "kernels.cuh"
+
+namespace b200lp {
+
+constexpr int ST_SPIN_TIMEOUT = -6;      // == B200LP_ERR_INTERNAL
+constexpr int kPLookMax = 16;            // look CTAs of k_persist
+constexpr int kPUnits = 4;               // double2 column units a look thread loads per batch
+
+struct alignas(16) PSync {
+    unsigned long long decided;          // decisions 1..decided are in the ring
+    unsigned long long done[kRing];      // done[k & 3]: tile CTAs that finished update(k), summed over uses
+    unsigned long long bar[2];           // look-grid barriers (monotonic arrival counts)
+    int abort;                           // != 0: some spin timed out; everyone leaves
+    int pad;
+    // telemetry, summed over decisions by look CTA 0 (ns of %globaltimer)
+    unsigned long long look_count, ns_look, ns_wait_done, ns_a, ns_b1, ns_xwait, ns_b2;
+    Cand part[2][kPLookMax];
+};
+
+// Exchange layout of the persistent loop (inside the same peer-mapped buffer k_iter uses):
+//   cand[kRing][kMaxWorld] x (kCandHdr + ld) doubles   header + scaled candidate row of every rank
+//   flag[kRing][kMaxWorld] u64                         "rank r's candidate for this slot has landed"
+__host__ __device__ __forceinline__ int64_t px_cand_off(int slot, int r, int64_t ld) { return (int64_t)(slot * kMaxWorld + r) * (kCandHdr + ld); }
+__host__ __device__ __forceinline__ int64_t px_flag_off(int slot, int r, int64_t ld) { return (int64_t)kRing * kMaxWorld * (kCandHdr + ld) + slot * kMaxWorld + r; }
+__host__ __device__ __forceinline__ int64_t px_words(int64_t ld) { return (int64_t)kRing * kMaxWorld * (kCandHdr + ld) + kRing * kMaxWorld + 8; }
+
+struct PersistArgs {
+    double *tab[2];           // tab[i & 1] holds S_i, the tableau after i pivots of this call
+    int64_t ld;
+    int C, m_local, R_local, row0, world, rank;
+    int is_max, rule, mode;   // mode 0: one shard; 2: peer-mapped exchange
+    double thr_enter, thr_pivot;
+    long long iters0;         // pivots completed before this call
+    long long max_iters;      // absolute cap on the pivot count; 0 = unlimited
+    IterState *ring;          // kRing decisions
+    double *colring;          // kRing x col_stride pivot-column snapshots
+    int64_t col_stride;
+    double *prowring;         // mode 0: kRing x prow_stride scaled pivot rows
+    int64_t prow_stride;
+    double *objc;             // ld doubles: running copy of the objective row
+    double *rhsc;             // R_local doubles: running copy of the RHS column
+    Xchg xchg;
+    int32_t *basis;
+    Report *report;
+    int2 *trace;
+    int trace_cap;
+    PSync *sync;
+    unsigned long long timeout_ns;
+    int look_ctas;
+    int slot_base;            // ring slot of decision k is (slot_base + k) & 3: the ring keeps turning
+                              // across calls, so a rank that is already in the next call never
+                              // overwrites a slot a slower rank's last update still reads
+};
+
+// ---- spins -------------------------------------------------------------------------------------
+__device__ __forceinline__ bool spin_ge(const unsigned long long *p, unsigned long long want,
+                                        PSync *S, unsigned long long timeout_ns, int code)
+{
+    const volatile unsigned long long *v = p;
+    if (*v >= want) return true;
+    const unsigned long long t0 = global_timer_ns();
+    for (;;) {
+        for (int k = 0; k < 32; ++k)
+            if (*v >= want) return true;
+        if (*reinterpret_cast<volatile int *>(&S->abort)) return false;
+        if (global_timer_ns() - t0 > timeout_ns) {
+            atomicCAS(&S->abort, 0, code);
+            return false;
+        }
+    }
+}
+
+// Thread 0 waits, everybody learns the outcome; data published before the flag is visible after.
+__device__ __forceinline__ bool cta_wait_ge(const unsigned long long *p, unsigned long long want,
+                                            PSync *S, unsigned long long timeout_ns, int code)
+{
+    int ok = 1;
+    if (threadIdx.x == 0) {
+        ok = spin_ge(p, want, S, timeout_ns, code) ? 1 : 0;
+        __threadfence();
+    }
+    return __syncthreads_and(ok) != 0;
+}
+
+// Barrier of the G look CTAs (co-resident: cooperative launch).  `target` = G x (uses so far).
+__device__ __forceinline__ bool look_bar(PSync *S, int which, unsigned long long target,
+                                         unsigned long long timeout_ns)
+{
+    __syncthreads();
+    int ok = 1;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&S->bar[which], 1ull);
+        ok = spin_ge(&S->bar[which], target, S, timeout_ns, ST_SPIN_TIMEOUT) ? 1 : 0;
+        __threadfence();
+    }
+    return __syncthreads_and(ok) != 0;
+}
+
+__device__ __forceinline__ Cand preduce(const Cand *part, int G, Cand *s_out)
+{
+    if (threadIdx.x < 32) {
+        Cand d;
+        d.q = 0.0; d.key = 0; d.row = -1;
+        if ((int)threadIdx.x < G) {
+            const Cand *p = part + threadIdx.x;
+            d.q = __ldcg(&p->q); d.key = __ldcg(&p->key); d.row = __ldcg(&p->row);
+        }
+        d = cand_warp_min(d);
+        if (threadIdx.x == 0) *s_out = d;
+    }
+    __syncthreads();
+    return *s_out;
+}
+
+__device__ __forceinline__ const double *p_prow(const PersistArgs &P, int slot, int w)
+{
+    if (P.mode == 2) return P.xchg.peer[P.rank] + px_cand_off(slot, w, P.ld) + kCandHdr;
+    return P.prowring + (int64_t)slot * P.prow_stride;
+}
+
+__device__ __forceinline__ double2 ldcg2(const double *p)
+{
+    return __ldcg(reinterpret_cast<const double2 *>(p));
+}
+__device__ __forceinline__ void stcg2(double *p, const double2 v)
+{
+    __stcg(reinterpret_cast<double2 *>(p), v);
+}
+
+// argmin bookkeeping of find-entering-column over one objective-row value
+__device__ __forceinline__ void enter_scan(Cand &best, const double o, const int cc, const int nv,
+                                           const int is_max, const int rule, const double thr)
+{
+    if (cc >= nv) return;
+    const double key = is_max ? o : -o;
+    if (rule == 0) {
+        // thread-local order is ascending in cc, so strict < keeps the first extremum
+        if (best.row < 0 || key < best.q) { best.q = key; best.key = cc; best.row = cc; }
+    } else if (best.row < 0 && key < 0.0 - thr) {
+        best.q = 0.0; best.key = cc; best.row = cc;              // Bland: lowest passing index
+    }
+}
+
+// ---- look role ---------------------------------------------------------------------------------
+__device__ __noinline__ void persist_look(const PersistArgs &P, const int cta, const int G)
+{
+    __shared__ Cand red[kLookThreads / 32];
+    __shared__ Cand s_part;
+    __shared__ int s_p, s_w;
+    const int tid = threadIdx.x;
+    PSync *S = P.sync;
+    const int nv = P.C - 1, rhs = P.C - 1;
+    const int ld = (int)P.ld, ldv = ld >> 1;
+    const bool lead = (cta == 0 && tid == 0);
+    const unsigned long long T = gridDim.x - G;
+    unsigned long long bar_n[2] = {0ull, 0ull};
+    const int chunkV = (ldv + G - 1) / G;
+    const int v_begin = cta * chunkV, v_end = min(ldv, v_begin + chunkV);
+    const int chunkR = (P.R_local + G - 1) / G;
+    const int r_begin = cta * chunkR, r_end = min(P.R_local, r_begin + chunkR);
+    const unsigned long long tl0 = global_timer_ns();
+
+    // ---- prologue: compact copies of S_0's objective row / RHS column; entering column of pivot 1
+    Cand best;
+    best.q = 0.0; best.key = 0; best.row = -1;
+    {
+        const double *S0 = P.tab[0];
+        const double *obj = S0 + (int64_t)P.m_local * P.ld;
+        for (int v = v_begin + tid; v < v_end; v += kLookThreads) {
+            const double2 o = ldcg2(obj + 2 * v);
+            stcg2(P.objc + 2 * v, o);
+            enter_scan(best, o.x, 2 * v, nv, P.is_max, P.rule, P.thr_enter);
+            enter_scan(best, o.y, 2 * v + 1, nv, P.is_max, P.rule, P.thr_enter);
+        }
+        for (int i = r_begin + tid; i < r_end; i += kLookThreads)
+            __stcg(P.rhsc + i, __ldcg(S0 + (int64_t)i * P.ld + rhs));
+    }
+    best = cand_block_min<kLookThreads>(best, red);
+    if (G > 1) {
+        if (tid == 0) S->part[1][cta] = best;
+        bar_n[1] += G;
+        if (!look_bar(S, 1, bar_n[1], P.timeout_ns)) return;
+        best = preduce(S->part[1], G, &s_part);
+    }
+    long long iters = P.iters0;
+    int j = -1;
+    {
+        const bool accept = (best.row >= 0) && (P.rule != 0 || best.q < 0.0 - P.thr_enter);
+        int fin = ST_RUNNING;
+        if (!accept) fin = ST_OPTIMAL;
+        else if (P.max_iters > 0 && iters >= P.max_iters) fin = ST_ITERATION_LIMIT;
+        j = accept ? best.row : -1;
+        if (fin != ST_RUNNING) {
+            if (lead) {
+                IterState o;
+                o.status = fin; o.j = j; o.p = -1; o.w = 0; o.iters = iters; o.pad = 0;
+                P.ring[(1 + P.slot_base) & (kRing - 1)] = o;
+                P.report->iters = iters;
+                P.report->status = fin;
+                __threadfence();
+                *reinterpret_cast<volatile unsigned long long *>(&S->decided) = 1ull;
+            }
+            return;
+        }
+    }
+
+    int j_prev = -1, p_prev = -1, w_prev = 0;
+    for (long long k = 1;; ++k) {
+        const int slot = (int)((k + P.slot_base) & (kRing - 1));
+        const int pslot = (int)((k - 1 + P.slot_base) & (kRing - 1));
+        const bool pending = k >= 2;
+        const double *src = P.tab[pending ? (int)(k & 1) : 0];       // S_{k-2} (S_0 for k = 1)
+        const unsigned long long t0 = lead ? global_timer_ns() : 0ull;
+        if (k >= 3) {
+            // S_{k-2} must be complete: every tile CTA has finished update(k-2)
+            const unsigned long long want = T * (unsigned long long)((k - 3) / kRing + 1);
+            if (!cta_wait_ge(&S->done[(k - 2) & (kRing - 1)], want, S, P.timeout_ns, ST_SPIN_TIMEOUT))
+                return;
+        }
+        const unsigned long long t1 = lead ? global_timer_ns() : 0ull;
+        const double *colp = P.colring + (int64_t)pslot * P.col_stride;
+        const double *prowp = p_prow(P, pslot, w_prev);
+        double *col_out = P.colring + (int64_t)slot * P.col_stride;
+        int pp_local = -1;
+        if (pending) {
+            const int rel = p_prev - P.row0;
+            if (rel >= 0 && rel < P.m_local) pp_local = rel;
+        }
+
+        // ---- phase A: pivot-column snapshot + ratio test over this shard's rows ---------------
+        Cand c;
+        c.q = 0.0; c.key = 0; c.row = -1;
+        {
+            const double pj = pending ? __ldcg(prowp + j) : 0.0;
+            const double pb = pending ? __ldcg(prowp + rhs) : 0.0;
+            for (int base = r_begin + tid; base < r_end; base += kLookRows * kLookThreads) {
+                double va[kLookRows], vb[kLookRows], vt[kLookRows];
+#pragma unroll
+                for (int u = 0; u < kLookRows; ++u) {
+                    const int i = base + u * kLookThreads;
+                    const bool in = i < r_end;
+                    va[u] = in ? __ldcg(src + (int64_t)i * P.ld + j) : 0.0;
+                    vb[u] = in ? __ldcg(P.rhsc + i) : 0.0;
+                    vt[u] = (pending && in) ? __ldcg(colp + i) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < kLookRows; ++u) {
+                    const int i = base + u * kLookThreads;
+                    if (i >= r_end) break;
+                    double a = va[u], b = vb[u];
+                    if (pending) {
+                        const double t = vt[u];
+                        a = (i == pp_local) ? pj : __dsub_rn(a, __dmul_rn(t, pj));
+                        b = (i == pp_local) ? pb : __dsub_rn(b, __dmul_rn(t, pb));
+                        __stcg(P.rhsc + i, b);                     // RHS column of S_{k-1}
+                    }
+                    __stcg(col_out + i, a);
+                    if (i < P.m_local && 0.0 + P.thr_pivot < a) {
+                        Cand d;
+                        d.q = __ddiv_rn(b, a);
+                        d.key = P.rule ? ((i == pp_local) ? j_prev : __ldcg(P.basis + i)) : P.row0 + i;
+                        d.row = P.row0 + i;
+                        c = cand_min(c, d);
+                    }
+                }
+            }
+        }
+        __syncthreads();                                           // red[] reuse
+        c = cand_block_min<kLookThreads>(c, red);
+        if (G > 1) {
+            if (tid == 0) S->part[0][cta] = c;
+            bar_n[0] += G;
+            if (!look_bar(S, 0, bar_n[0], P.timeout_ns)) return;
+            c = preduce(S->part[0], G, &s_part);
+        }
+        const unsigned long long t2 = lead ? global_timer_ns() : 0ull;
+        unsigned long long t3 = t2, t4 = t2;
+
+        // ---- phase B: candidate row / pivot element, objective-row update, next entering column
+        int p = c.row, w = 0;
+        best.q = 0.0; best.key = 0; best.row = -1;
+        const double tobj = __ldcg(col_out + P.m_local);           // objective-row entry of column j
+        if (P.mode != 2) {
+            if (p >= 0) {
+                const int i = p - P.row0;
+                const double s = __ldcg(col_out + i);
+                const double t = pending ? __ldcg(colp + i) : 0.0;
+                const bool is_pp = pending && (i == pp_local);
+                const double *rowp = src + (int64_t)i * P.ld;
+                double *prow_out = P.prowring + (int64_t)slot * P.prow_stride;
+                for (int base = v_begin + tid; base < v_end; base += kPUnits * kLookThreads) {
+                    double2 vr[kPUnits], vp[kPUnits], vo[kPUnits];
+#pragma unroll
+                    for (int u = 0; u < kPUnits; ++u) {
+                        const int v = base + u * kLookThreads;
+                        const bool in = v < v_end;
+                        vr[u] = (in && !is_pp) ? ldcg2(rowp + 2 * v) : make_double2(0.0, 0.0);
+                        vp[u] = (in && pending) ? ldcg2(prowp + 2 * v) : make_double2(0.0, 0.0);
+                        vo[u] = in ? ldcg2(P.objc + 2 * v) : make_double2(0.0, 0.0);
+                    }
+#pragma unroll
+                    for (int u = 0; u < kPUnits; ++u) {
+                        const int v = base + u * kLookThreads;
+                        if (v >= v_end) break;
+                        double x0 = vr[u].x, x1 = vr[u].y;
+                        if (pending) {
+                            x0 = is_pp ? vp[u].x : __dsub_rn(x0, __dmul_rn(t, vp[u].x));
+                            x1 = is_pp ? vp[u].y : __dsub_rn(x1, __dmul_rn(t, vp[u].y));
+                        }
+                        x0 = (2 * v < P.C) ? __ddiv_rn(x0, s) : 0.0;
+                        x1 = (2 * v + 1 < P.C) ? __ddiv_rn(x1, s) : 0.0;
+                        double2 o;
+                        o.x = __dsub_rn(vo[u].x, __dmul_rn(tobj, x0));
+                        o.y = __dsub_rn(vo[u].y, __dmul_rn(tobj, x1));
+                        stcg2(prow_out + 2 * v, make_double2(x0, x1));
+                        stcg2(P.objc + 2 * v, o);
+                        enter_scan(best, o.x, 2 * v, nv, P.is_max, P.rule, P.thr_enter);
+                        enter_scan(best, o.y, 2 * v + 1, nv, P.is_max, P.rule, P.thr_enter);
+                    }
+                }
+            }
+        } else {
+            // B1: scale OUR candidate row and push header + row to every rank (one flag each)
+            const unsigned long long seq = P.xchg.epoch + (unsigned long long)k;
+            if (p >= 0) {
+                const int i = p - P.row0;
+                const double s = __ldcg(col_out + i);
+                const double t = pending ? __ldcg(colp + i) : 0.0;
+                const bool is_pp = pending && (i == pp_local);
+                const double *rowp = src + (int64_t)i * P.ld;
+                const int64_t off = px_cand_off(slot, P.rank, P.ld) + kCandHdr;
+                for (int base = v_begin + tid; base < v_end; base += kPUnits * kLookThreads) {
+                    double2 vr[kPUnits], vp[kPUnits];
+#pragma unroll
+                    for (int u = 0; u < kPUnits; ++u) {
+                        const int v = base + u * kLookThreads;
+                        const bool in = v < v_end;
+                        vr[u] = (in && !is_pp) ? ldcg2(rowp + 2 * v) : make_double2(0.0, 0.0);
+                        vp[u] = (in && pending) ? ldcg2(prowp + 2 * v) : make_double2(0.0, 0.0);
+                    }
+#pragma unroll
+                    for (int u = 0; u < kPUnits; ++u) {
+                        const int v = base + u * kLookThreads;
+                        if (v >= v_end) break;
+                        double x0 = vr[u].x, x1 = vr[u].y;
+                        if (pending) {
+                            x0 = is_pp ? vp[u].x : __dsub_rn(x0, __dmul_rn(t, vp[u].x));
+                            x1 = is_pp ? vp[u].y : __dsub_rn(x1, __dmul_rn(t, vp[u].y));
+                        }
+                        x0 = (2 * v < P.C) ? __ddiv_rn(x0, s) : 0.0;
+                        x1 = (2 * v + 1 < P.C) ? __ddiv_rn(x1, s) : 0.0;
+                        const double2 x = make_double2(x0, x1);
+                        for (int g = 0; g < P.world; ++g)
+                            *reinterpret_cast<double2 *>(P.xchg.peer[g] + off + 2 * v) = x;
+                    }
+                }
+                __threadfence_system();
+            }
+            if (G > 1) {                                           // every CTA's slice is on its way
+                bar_n[1] += G;
+                if (!look_bar(S, 1, bar_n[1], P.timeout_ns)) return;
+            } else {
+                __syncthreads();
+            }
+            if (cta == 0 && tid < P.world) {
+                double *h = P.xchg.peer[tid] + px_cand_off(slot, P.rank, P.ld);
+                h[0] = c.q;
+                reinterpret_cast<long long *>(h)[1] = c.key;
+                reinterpret_cast<long long *>(h)[2] = c.row;
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned long long *>(
+                    P.xchg.peer[tid] + px_flag_off(slot, P.rank, P.ld)) = seq;
+            }
+            t3 = lead ? global_timer_ns() : 0ull;
+            // B2: ONE wait for every rank's candidate, then the same winner everywhere
+            {
+                int ok = 1;
+                if (tid < P.world) {
+                    const unsigned long long *f = reinterpret_cast<const unsigned long long *>(
+                        P.xchg.peer[P.rank] + px_flag_off(slot, tid, P.ld));
+                    ok = spin_ge(f, seq, S, P.timeout_ns, ST_PEER_TIMEOUT) ? 1 : 0;
+                    __threadfence_system();
+                }
+                if (!__syncthreads_and(ok)) return;
+            }
+            if (tid == 0) {
+                int ww = 0;
+                s_p = resolve_winner(P.xchg.peer[P.rank] + px_cand_off(slot, 0, P.ld),
+                                     kCandHdr + P.ld, P.world, &ww).row;
+                s_w = ww;
+            }
+            __syncthreads();
+            p = s_p; w = s_w;
+            t4 = lead ? global_timer_ns() : 0ull;
+            if (p >= 0) {
+                const double *prow_k = p_prow(P, slot, w);
+                for (int base = v_begin + tid; base < v_end; base += kPUnits * kLookThreads) {
+                    double2 vp[kPUnits], vo[kPUnits];
+#pragma unroll
+                    for (int u = 0; u < kPUnits; ++u) {
+                        const int v = base + u * kLookThreads;
+                        const bool in = v < v_end;
+                        vp[u] = in ? ldcg2(prow_k + 2 * v) : make_double2(0.0, 0.0);
+                        vo[u] = in ? ldcg2(P.objc + 2 * v) : make_double2(0.0, 0.0);
+                    }
+#pragma unroll
+                    for (int u = 0; u < kPUnits; ++u) {
+                        const int v = base + u * kLookThreads;
+                        if (v >= v_end) break;
+                        double2 o;
+                        o.x = __dsub_rn(vo[u].x, __dmul_rn(tobj, vp[u].x));
+                        o.y = __dsub_rn(vo[u].y, __dmul_rn(tobj, vp[u].y));
+                        stcg2(P.objc + 2 * v, o);
+                        enter_scan(best, o.x, 2 * v, nv, P.is_max, P.rule, P.thr_enter);
+                        enter_scan(best, o.y, 2 * v + 1, nv, P.is_max, P.rule, P.thr_enter);
+                    }
+                }
+            }
+        }
+        if (p < 0) {                                               // no eligible row anywhere: unbounded
+            if (lead) {
+                IterState o;
+                o.status = ST_UNBOUNDED; o.j = j; o.p = -1; o.w = 0; o.iters = iters; o.pad = 0;
+                P.ring[slot] = o;
+                P.report->iters = iters;
+                P.report->status = ST_UNBOUNDED;
+                __threadfence();
+                *reinterpret_cast<volatile unsigned long long *>(&S->decided) = (unsigned long long)k;
+            }
+            return;
+        }
+        __syncthreads();                                           // red[] reuse
+        best = cand_block_min<kLookThreads>(best, red);
+        if (G > 1) {
+            if (tid == 0) S->part[1][cta] = best;
+            bar_n[1] += G;
+            if (!look_bar(S, 1, bar_n[1], P.timeout_ns)) return;
+            best = preduce(S->part[1], G, &s_part);
+        }
+        // the scaled pivot row is complete (every look CTA passed the barrier): publish pivot k
+        const long long iters_after = iters + 1;
+        const bool accept = (best.row >= 0) && (P.rule != 0 || best.q < 0.0 - P.thr_enter);
+        int fin = ST_RUNNING;
+        if (!accept) fin = ST_OPTIMAL;
+        else if (P.max_iters > 0 && iters_after >= P.max_iters) fin = ST_ITERATION_LIMIT;
+        const int jn = accept ? best.row : -1;
+        if (lead) {
+            const int rel = p - P.row0;
+            if (rel >= 0 && rel < P.m_local) P.basis[rel] = j;      // (setf (aref basis p) j) :358
+            if (P.trace && iters < P.trace_cap) P.trace[iters] = make_int2(j, p);
+            IterState o;
+            o.status = ST_RUNNING; o.j = j; o.p = p; o.w = w; o.iters = iters; o.pad = 0;
+            P.ring[slot] = o;
+            if (fin != ST_RUNNING) {
+                IterState e;
+                e.status = fin; e.j = jn; e.p = -1; e.w = 0; e.iters = iters_after; e.pad = 0;
+                P.ring[(k + 1 + P.slot_base) & (kRing - 1)] = e;
+                P.report->iters = iters_after;
+                P.report->status = fin;
+            }
+            __threadfence();
+            *reinterpret_cast<volatile unsigned long long *>(&S->decided) =
+                (unsigned long long)(fin != ST_RUNNING ? k + 1 : k);
+            const unsigned long long t5 = global_timer_ns();
+            S->look_count += 1;
+            S->ns_wait_done += t1 - t0;
+            S->ns_a += t2 - t1;
+            S->ns_b1 += t3 - t2;
+            S->ns_xwait += t4 - t3;
+            S->ns_b2 += t5 - t4;
+            S->ns_look = t5 - tl0;
+        }
+        if (fin != ST_RUNNING) return;
+        j_prev = j; p_prev = p; w_prev = w;
+        j = jn;
+        iters = iters_after;
+    }
+}
+
+// ---- tile role -----------------------------------------------------------------------------------
+// Chunk of rows [ra, rb) of column tile tx: n-pivot-row part 2 for 256 double2 columns.
+template <int UNROLL, bool STREAM>
+__device__ __forceinline__ void persist_chunk(const double2 *src2, double2 *dst2, const int ldv,
+                                              const int tx, const int ra, const int rb,
+                                              const double *col, const double *prow,
+                                              const int p_local)
+{
+    const int cv = tx * kPivotThreads + (int)threadIdx.x;
+    const bool act = cv < ldv;
+    const int lane = threadIdx.x & 31;
+    const double2 pr = act ? ldcg2(prow + 2 * cv) : make_double2(0.0, 0.0);
+    for (int r = ra; r < rb; r += UNROLL) {
+        double cl = 0.0;
+        if (lane < UNROLL && r + lane < rb) cl = __ldcg(col + r + lane);
+        double2 a[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+            if (act && r + u < rb) a[u] = ld_tab<STREAM>(src2 + (int64_t)(r + u) * ldv + cv);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const double t = __shfl_sync(0xffffffffu, cl, u);
+            if (act && r + u < rb) {
+                double2 o;
+                o.x = __dsub_rn(a[u].x, __dmul_rn(t, pr.x));
+                o.y = __dsub_rn(a[u].y, __dmul_rn(t, pr.y));
+                if (r + u == p_local) o = pr;
+                st_tab<STREAM>(dst2 + (int64_t)(r + u) * ldv + cv, o);
+            }
+        }
+    }
+}
+
+template <int UNROLL, bool STREAM>
+__device__ __forceinline__ void persist_tiles(const PersistArgs &P, const int tcta, const int T)
+{
+    __shared__ int s_status, s_pw[2];
+    PSync *S = P.sync;
+    const int ldv = (int)(P.ld >> 1);
+    const int tiles_x = (ldv + kPivotThreads - 1) / kPivotThreads;
+    // balanced contiguous share of the (column tile, row) space, column-tile major
+    const long long U = (long long)tiles_x * P.R_local;
+    const long long u0 = U * tcta / T, u1 = U * (tcta + 1) / T;
+    for (long long k = 1;; ++k) {
+        const int slot = (int)((k + P.slot_base) & (kRing - 1));
+        int ok = 1;
+        if (threadIdx.x == 0) {
+            ok = spin_ge(&S->decided, (unsigned long long)k, S, P.timeout_ns, ST_SPIN_TIMEOUT) ? 1 : 0;
+            __threadfence();
+            const volatile IterState *st = P.ring + slot;
+            s_status = st->status;
+            s_pw[0] = st->p;
+            s_pw[1] = st->w;
+        }
+        if (!__syncthreads_and(ok)) return;
+        if (s_status != ST_RUNNING) return;
+        const int p = s_pw[0], w = s_pw[1];
+        const int rel = p - P.row0;
+        const int p_local = (rel >= 0 && rel < P.m_local) ? rel : -1;
+        const double2 *src2 = reinterpret_cast<const double2 *>(P.tab[(k - 1) & 1]);
+        double2 *dst2 = reinterpret_cast<double2 *>(P.tab[k & 1]);
+        const double *col = P.colring + (int64_t)slot * P.col_stride;
+        const double *prow = p_prow(P, slot, w);
+        for (long long u = u0; u < u1;) {
+            const int tx = (int)(u / P.R_local);
+            const int ra = (int)(u - (long long)tx * P.R_local);
+            const int rb = (int)min((long long)P.R_local, ra + (u1 - u));
+            persist_chunk<UNROLL, STREAM>(src2, dst2, ldv, tx, ra, rb, col, prow, p_local);
+            u += rb - ra;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(&S->done[k & (kRing - 1)], 1ull);
+        }
+    }
+}
+
+template <int UNROLL, bool STREAM>
+__global__ void __launch_bounds__(kPivotThreads, 2) k_persist(const __grid_constant__ PersistArgs P)
+{
+    const int G = P.look_ctas;
+    if ((int)blockIdx.x < G) persist_look(P, blockIdx.x, G);
+    else persist_tiles<UNROLL, STREAM>(P, (int)blockIdx.x - G, (int)gridDim.x - G);
+}
+
+} // namespace b200lp

@@ -27,6 +27,7 @@
 
 #include "../../include/b200lp.h"
 #include "kernels.cuh"
+#include "persist.cuh"
 #include "nccl_dyn.h"
 
 namespace b200lp {
@@ -131,6 +132,13 @@ struct Shard {
     std::vector<cudaEvent_t> ev_pivot; // pairs
     std::vector<cudaEvent_t> ev_lookt; // triples: before look, after look, after exchange
     int ratio_blocks = 0;
+    // persistent cooperative loop (persist.cuh)
+    double *objc = nullptr;     // ld doubles: running objective row of the look role
+    double *rhsc = nullptr;     // R_local doubles: running RHS column
+    PSync *psync = nullptr;
+    int coop = 0;               // cudaDevAttrCooperativeLaunch
+    int sm_count = 0;
+    int plook_ctas = 1;
 };
 
 } // namespace b200lp
@@ -156,6 +164,9 @@ struct b200lp_solver {
     int xmode = 0;
     unsigned long long epoch = 0;
     unsigned long long peer_timeout_ns = 120ull * 1000 * 1000 * 1000;   // B200LP_PEER_TIMEOUT_MS
+    unsigned long long spin_timeout_ns = 20ull * 1000 * 1000 * 1000;    // B200LP_SPIN_TIMEOUT_MS
+    unsigned long long ring_base = 0;   // decisions published so far (persistent loop's ring position)
+    int last_loop = 0;                  // 1 = k_iter per pivot, 2 = k_persist
 };
 
 namespace b200lp {
@@ -184,6 +195,13 @@ static void shape_shard(Shard &sh)
     sh.iter_ctas = 0;
     sh.ratio_blocks = (sh.R_local + kRatioThreads - 1) / kRatioThreads;
     sh.xchg.ld = sh.ld;
+    // persistent loop: one look CTA while a row is short (no look-grid barriers at all), else
+    // enough that a look thread touches only a few 16-byte units per phase
+    sh.plook_ctas = sh.ld <= 4096 ? 1 : (int)std::min<int64_t>(kPLookMax, std::max<int64_t>(2, (sh.ld + 2047) / 2048));
+    if (const char *e = getenv("B200LP_LOOK_CTAS")) {
+        const int g = atoi(e);
+        if (g >= 1 && g <= kPLookMax) sh.plook_ctas = g;
+    }
 }
 
 static int ensure_trace(b200lp_solver *s, Shard &sh)
@@ -225,9 +243,15 @@ static int alloc_shard(b200lp_solver *s, Shard &sh)
     if (s->world > 1) {
         CU_TRY(cudaMalloc(&sh.gathring, sizeof(double) * stride * s->world * kRing));
         CU_TRY(cudaMemsetAsync(sh.gathring, 0, sizeof(double) * stride * s->world * kRing, sh.stream));
-        CU_TRY(cudaMalloc(&sh.xbuf, sizeof(double) * xchg_words(sh.ld)));
-        CU_TRY(cudaMemsetAsync(sh.xbuf, 0, sizeof(double) * xchg_words(sh.ld), sh.stream));
+        const int64_t xw = std::max(xchg_words(sh.ld), px_words(sh.ld));
+        CU_TRY(cudaMalloc(&sh.xbuf, sizeof(double) * xw));
+        CU_TRY(cudaMemsetAsync(sh.xbuf, 0, sizeof(double) * xw, sh.stream));
     }
+    CU_TRY(cudaMalloc(&sh.objc, sizeof(double) * sh.cap_ld));
+    CU_TRY(cudaMalloc(&sh.rhsc, sizeof(double) * sh.cap_rows));
+    CU_TRY(cudaMalloc(&sh.psync, sizeof(PSync)));
+    CU_TRY(cudaDeviceGetAttribute(&sh.coop, cudaDevAttrCooperativeLaunch, sh.device));
+    CU_TRY(cudaDeviceGetAttribute(&sh.sm_count, cudaDevAttrMultiProcessorCount, sh.device));
     std::memset(&sh.xchg, 0, sizeof(sh.xchg));
     sh.xchg.rank = sh.rank; sh.xchg.world = s->world; sh.xchg.ld = sh.ld;
     sh.colbuf = sh.colring;
@@ -268,6 +292,7 @@ static void free_shard(Shard &sh)
     cudaFree(sh.colring); cudaFree(sh.candring); cudaFree(sh.gathring); cudaFree(sh.xbuf);
     cudaFree(sh.ring); cudaFree(sh.report); cudaFree(sh.look_sync);
     cudaFree(sh.partials); cudaFree(sh.st);
+    cudaFree(sh.objc); cudaFree(sh.rhsc); cudaFree(sh.psync);
     cudaFree(sh.trace);
     if (sh.h_report) cudaFreeHost(sh.h_report);
     for (int k = 0; k < 4; ++k) {
@@ -685,17 +710,202 @@ static int default_poll_interval(const b200lp_solver *s)
     return 32;
 }
 
-// n-solve-tableau's loop, src/simplex.lisp:455-460, for at most `limit` more pivots.
-// Iteration k = { update(k) on the main stream || look(k -> k+1) on the look stream }; the host
-// enqueues a batch ahead and polls the device Report one batch behind, so neither stream drains.
-static int iterate_locked(b200lp_solver *s, int64_t limit, b200lp_result *out, int32_t *trace_j,
-                          int32_t *trace_r)
+// ---- persistent cooperative loop (persist.cuh) ---------------------------------------------------
+// variant -> (UNROLL, STREAM) of k_persist's tile role
+#define B200LP_PVARIANTS(X) \
+    switch (v) {                   \
+    default:                       \
+    case 20: X(16, true); break;   \
+    case 21: X(16, false); break;  \
+    case 22: X(8, true); break;    \
+    case 23: X(8, false); break;   \
+    }
+
+static int pick_pvariant(const b200lp_solver *s, const Shard &sh)
+{
+    const int v = s->opts.pivot_variant;
+    if (v >= 20 && v <= 23) return v;
+    // both ping-pong buffers L2 resident: default caching; larger tableaus stream (evict-first)
+    const double bytes = 8.0 * (double)sh.ld * sh.R_local;
+    return bytes > 48e6 ? 20 : 21;
+}
+
+static int loop_env()
+{
+    const char *e = getenv("B200LP_LOOP");       // iter | persist; default: persist where possible
+    if (!e) return 0;
+    if (std::strcmp(e, "iter") == 0) return 1;
+    if (std::strcmp(e, "persist") == 0) return 2;
+    return 0;
+}
+
+// The persistent loop serves one shard or the peer-mapped exchange; the NCCL fallback (xmode 1)
+// and explicitly requested k_iter tile variants (1..13, the variant sweep) use the per-pivot loop.
+static bool want_persist(const b200lp_solver *s)
+{
+    if (s->xmode == 1 || loop_env() == 1) return false;
+    const int v = s->opts.pivot_variant;
+    if (v >= 1 && v < 20 && loop_env() != 2) return false;
+    for (const Shard &sh : s->shards)
+        if (!sh.coop) return false;
+    return true;
+}
+
+template <int UNROLL, bool STREAM>
+static cudaError_t launch_persist_t(Shard &sh, PersistArgs &a)
+{
+    static int occ = 0;                                   // CTAs per SM, same on every device here
+    if (occ == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &occ, k_persist<UNROLL, STREAM>, kPivotThreads, 0);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) return cudaErrorLaunchOutOfResources;
+    }
+    int grid = occ * sh.sm_count;
+    if (a.look_ctas >= grid) a.look_ctas = 1;
+    void *params[] = {&a};
+    return cudaLaunchCooperativeKernel((const void *)k_persist<UNROLL, STREAM>, dim3((unsigned)grid),
+                                       dim3(kPivotThreads), params, 0, sh.stream);
+}
+
+static int iterate_persist(b200lp_solver *s, int64_t limit, b200lp_result *out, int32_t *trace_j,
+                           int32_t *trace_r)
 {
     const double t0 = now_ms();
     if (limit <= 0) limit = s->opts.max_iters;
     const long long start_iters = s->iters_done;
     const long long cap = limit > 0 ? start_iters + limit : 0;
     const int64_t launches0 = s->kernel_launches;
+    s->epoch += 1ull << 40;                                // fresh flag values for this call
+    s->last_loop = 2;
+    for (Shard &sh : s->shards) {
+        CU_TRY(cudaSetDevice(sh.device));
+        if (!sh.tabs[1]) CU_TRY(cudaMalloc(&sh.tabs[1], sizeof(double) * sh.cap_ld * sh.cap_rows));
+        Report rep;
+        rep.status = ST_RUNNING; rep.pad = 0; rep.iters = start_iters;
+        CU_TRY(cudaMemcpyAsync(sh.report, &rep, sizeof(rep), cudaMemcpyHostToDevice, sh.stream));
+        CU_TRY(cudaMemsetAsync(sh.psync, 0, sizeof(PSync), sh.stream));
+    }
+    Shard &s0 = s->shards[0];
+    CU_TRY(cudaSetDevice(s0.device));
+    CU_TRY(cudaEventRecord(s0.ev_begin, s0.stream));
+    for (Shard &sh : s->shards) {
+        CU_TRY(cudaSetDevice(sh.device));
+        PersistArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.tab[0] = sh.tabs[sh.cur]; a.tab[1] = sh.tabs[sh.cur ^ 1];
+        a.ld = sh.ld;
+        a.C = (int)s->C; a.m_local = sh.m_local; a.R_local = sh.R_local; a.row0 = (int)sh.row0;
+        a.world = s->world; a.rank = sh.rank; a.is_max = s->is_max; a.rule = s->opts.pivot_rule;
+        a.mode = s->xmode;
+        a.thr_enter = s->thr_enter; a.thr_pivot = s->thr_pivot;
+        a.iters0 = start_iters; a.max_iters = cap;
+        a.ring = sh.ring; a.colring = sh.colring; a.col_stride = sh.R_local;
+        a.prowring = sh.candring + kCandHdr; a.prow_stride = kCandHdr + sh.ld;
+        a.objc = sh.objc; a.rhsc = sh.rhsc;
+        a.xchg = sh.xchg; a.xchg.epoch = s->epoch;
+        a.basis = sh.basis; a.report = sh.report;
+        a.trace = sh.trace; a.trace_cap = s->opts.trace_capacity;
+        a.sync = sh.psync;
+        a.timeout_ns = s->world > 1 ? std::max(s->peer_timeout_ns, s->spin_timeout_ns) : s->spin_timeout_ns;
+        a.look_ctas = sh.plook_ctas;
+        a.slot_base = (int)(s->ring_base & (kRing - 1));
+        const int v = pick_pvariant(s, sh);
+#define X(UN, ST) CU_TRY((launch_persist_t<UN, ST>(sh, a)))
+        B200LP_PVARIANTS(X)
+#undef X
+        s->kernel_launches++;
+    }
+    CU_TRY(cudaSetDevice(s0.device));
+    CU_TRY(cudaEventRecord(s0.ev_end, s0.stream));
+    for (Shard &sh : s->shards) {
+        CU_TRY(cudaSetDevice(sh.device));
+        CU_TRY(cudaStreamSynchronize(sh.stream));
+    }
+    CU_TRY(cudaSetDevice(s0.device));
+    Report last;
+    PSync ps;
+    std::memset(&ps, 0, sizeof(ps));
+    CU_TRY(cudaMemcpy(&last, s0.report, sizeof(last), cudaMemcpyDeviceToHost));
+    int aborted = 0;
+    for (Shard &sh : s->shards) {                          // any shard's abort fails the call
+        PSync q;
+        CU_TRY(cudaSetDevice(sh.device));
+        CU_TRY(cudaMemcpy(&q, sh.psync, sizeof(q), cudaMemcpyDeviceToHost));
+        if (&sh == &s0) ps = q;
+        if (q.abort && !aborted) aborted = q.abort;
+    }
+    CU_TRY(cudaSetDevice(s0.device));
+    if (aborted == ST_PEER_TIMEOUT)
+        return fail(B200LP_ERR_PEER_TIMEOUT, "iterate", "a peer GPU's candidate never arrived");
+    if (aborted)
+        return fail(B200LP_ERR_INTERNAL, "iterate", "a wait inside the persistent loop timed out");
+    if (last.status == ST_RUNNING)
+        return fail(B200LP_ERR_INTERNAL, "iterate", "device loop ended without a verdict");
+    const long long done = last.iters - start_iters;
+    s->iters_done = last.iters;
+    s->ring_base += (unsigned long long)done + 1ull;
+    for (Shard &sh : s->shards) {                          // pivots ping-pong between the buffers
+        sh.cur = (sh.cur + (int)(done & 1)) & 1;
+        sh.tab = sh.tabs[sh.cur];
+    }
+    const int status = last.status;
+    if (out) {
+        std::memset(out, 0, sizeof(*out));
+        out->status = status;
+        out->n_devices = s->world;
+        out->exchange_mode = s->xmode;
+        out->loop_mode = 2;
+        out->look_ctas = s0.plook_ctas;
+        out->iterations = done;
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, s0.ev_begin, s0.ev_end));
+        out->ms_solve = ms;
+        out->ms_look_kernel = (double)(ps.ns_wait_done + ps.ns_a + ps.ns_b1 + ps.ns_xwait + ps.ns_b2) * 1e-6;
+        out->look_kernel_launches = (int64_t)ps.look_count;
+        out->ms_look_wait = (double)ps.ns_wait_done * 1e-6;
+        out->ms_look_ratio = (double)ps.ns_a * 1e-6;
+        out->ms_look_push = (double)ps.ns_b1 * 1e-6;
+        out->ms_look_peer_wait = (double)ps.ns_xwait * 1e-6;
+        out->ms_look_row = (double)ps.ns_b2 * 1e-6;
+        out->kernel_launches = s->kernel_launches - launches0;
+        out->bytes_per_pivot = 16 * (int64_t)s0.R_local * s->C;
+        double obj = 0.0;
+        CU_TRY(cudaMemcpy(&obj, s0.tab + (int64_t)s0.m_local * s0.ld + (s->C - 1), sizeof(double),
+                          cudaMemcpyDeviceToHost));
+        out->objective = obj;
+        out->d2h_bytes += sizeof(double);
+        int tl = 0;
+        if (s->opts.trace_capacity > 0 && s0.trace) {
+            tl = (int)std::min<long long>(s->iters_done, s->opts.trace_capacity);
+            if (tl > 0 && (trace_j || trace_r)) {
+                CU_TRY(cudaMemcpy(s0.h_trace, s0.trace, sizeof(int2) * tl, cudaMemcpyDeviceToHost));
+                for (int q = 0; q < tl; ++q) {
+                    if (trace_j) trace_j[q] = s0.h_trace[q].x;
+                    if (trace_r) trace_r[q] = s0.h_trace[q].y;
+                }
+                out->d2h_bytes += sizeof(int2) * tl;
+            }
+        }
+        out->trace_len = tl;
+        out->ms_total = now_ms() - t0;
+    }
+    return status;
+}
+
+// n-solve-tableau's loop, src/simplex.lisp:455-460, for at most `limit` more pivots.
+// Iteration k = { update(k) on the main stream || look(k -> k+1) on the look stream }; the host
+// enqueues a batch ahead and polls the device Report one batch behind, so neither stream drains.
+static int iterate_locked(b200lp_solver *s, int64_t limit, b200lp_result *out, int32_t *trace_j,
+                          int32_t *trace_r)
+{
+    if (want_persist(s)) return iterate_persist(s, limit, out, trace_j, trace_r);
+    const double t0 = now_ms();
+    if (limit <= 0) limit = s->opts.max_iters;
+    const long long start_iters = s->iters_done;
+    const long long cap = limit > 0 ? start_iters + limit : 0;
+    const int64_t launches0 = s->kernel_launches;
+    s->last_loop = 1;
     s->ev_used = 0;
     s->evl_used = 0;
     const bool fused = s->xmode != 1;
@@ -804,6 +1014,8 @@ static int iterate_locked(b200lp_solver *s, int64_t limit, b200lp_result *out, i
         out->status = status;
         out->n_devices = s->world;
         out->exchange_mode = s->xmode;
+        out->loop_mode = 1;
+        out->look_ctas = s0.look_ctas;
         out->iterations = done;
         float ms = 0.f;
         CU_TRY(cudaEventElapsedTime(&ms, s0.ev_begin, s0.ev_end));
@@ -1092,6 +1304,10 @@ static int create_common(const b200lp_opts *opts, int64_t R, int64_t C, int32_t 
     if (opts) s->opts = *opts; else std::memset(&s->opts, 0, sizeof(s->opts));
     s->R = R; s->C = C; s->m = R - 1; s->is_max = is_max ? 1 : 0;
     fill_thresholds(s);
+    if (const char *t = getenv("B200LP_SPIN_TIMEOUT_MS")) {
+        const long long ms = atoll(t);
+        if (ms > 0) s->spin_timeout_ns = (unsigned long long)ms * 1000000ull;
+    }
     *out = s;
     return B200LP_OK;
 }

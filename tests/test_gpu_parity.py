@@ -206,14 +206,36 @@ def test_fp_tolerance_keyword_changes_thresholds_like_the_oracle():
         assert np.array_equal(g_tab, o_tab)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 20, 21, 22, 23])
 def test_every_pivot_kernel_variant_is_bit_exact(variant):
+    """1..13: one k_iter launch per pivot, every tile shape; 20..23: the persistent cooperative
+    loop (k_persist), every tile-role variant."""
     tab, basis = random_tableau(150, 333, seed=77)     # odd C, rows not a multiple of any tile
     o_tab, o_basis = tab.copy(), basis.copy()
     ost, oit, _ = oracle.solve(o_tab, o_basis, True)
     st, res, _ = _ffi.solve(tab, basis, True, _ffi.make_opts(writeback_full=True,
                                                              pivot_variant=variant))
     assert st == ost and res.iterations == oit and np.array_equal(tab, o_tab)
+    assert res.loop_mode == (2 if variant >= 20 else 1)
+
+
+@pytest.mark.parametrize("look_ctas", [1, 2, 5, 16])
+@pytest.mark.parametrize("m,n,rule", [(700, 3500, 0), (90, 5000, 1), (3000, 200, 0)])
+def test_persistent_loop_any_look_grid_is_bit_exact(m, n, rule, look_ctas, monkeypatch):
+    """k_persist with 1..16 look CTAs (the look-grid barriers and the per-CTA partial argmins):
+    status, pivot trace, basis and every cell equal the oracle's."""
+    monkeypatch.setenv("B200LP_LOOK_CTAS", str(look_ctas))
+    tab, basis = random_tableau(m, n, seed=m + n, signed=True)
+    o_tab, o_basis = tab.copy(), basis.copy()
+    cap = 600
+    ost, oit, otrace = oracle.solve(o_tab, o_basis, True, rule=rule, max_iters=cap, trace_cap=cap,
+                                    parallel=True)
+    st, res, trace = _ffi.solve(tab, basis, True,
+                                _ffi.make_opts(pivot_rule=rule, max_iters=cap, trace_capacity=cap,
+                                               writeback_full=True, pivot_variant=20))
+    assert (st, res.iterations) == (ost, oit) and trace == otrace
+    assert res.loop_mode == 2 and res.look_ctas == look_ctas
+    assert np.array_equal(basis, o_basis) and np.array_equal(tab, o_tab)
 
 
 # ------------------------------------------------------------------ degenerate / Bland (config 5)

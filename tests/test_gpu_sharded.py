@@ -26,14 +26,16 @@ needs2 = pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
 
 
 @needs2
-@pytest.mark.parametrize("exchange,mode", [("p2p", 2), ("nccl", 1)])
-@pytest.mark.parametrize("ndev,m,n", [(2, 200, 300), (2, 33, 20), (4, 130, 257), (8, 64, 96)])
-def test_in_process_multi_device_bit_exact(ndev, m, n, exchange, mode, monkeypatch):
-    """Both ways the candidate pivot rows travel: peer-mapped buffers written inside the
-    iteration kernel (default) and the NCCL all-gather fallback."""
+@pytest.mark.parametrize("exchange,mode,loop", [("p2p", 2, "persist"), ("p2p", 2, "iter"), ("nccl", 1, "iter")])
+@pytest.mark.parametrize("ndev,m,n", [(2, 200, 300), (2, 33, 20), (4, 130, 257), (8, 64, 96), (2, 300, 5000)])
+def test_in_process_multi_device_bit_exact(ndev, m, n, exchange, mode, loop, monkeypatch):
+    """Every way the candidate pivot rows travel: peer-mapped buffers written by the persistent
+    cooperative loop (default; one speculative push + one flag wait per pivot), peer-mapped
+    buffers written inside the per-pivot iteration kernel, and the NCCL all-gather fallback."""
     if _ngpu() < ndev:
         pytest.skip(f"needs {ndev} GPUs")
     monkeypatch.setenv("B200LP_EXCHANGE", exchange)
+    monkeypatch.setenv("B200LP_LOOP", loop)
     monkeypatch.setenv("B200LP_PEER_TIMEOUT_MS", "5000")
     tab, basis = synthetic.dense_tableau(m, n, seed=13)
     o_tab, o_basis = tab.copy(), basis.copy()
@@ -42,13 +44,13 @@ def test_in_process_multi_device_bit_exact(ndev, m, n, exchange, mode, monkeypat
                                 _ffi.make_opts(devices=list(range(ndev)), writeback_full=True,
                                                trace_capacity=1 << 16))
     assert st == ost and res.iterations == oit and res.n_devices == ndev
-    assert res.exchange_mode == mode
+    assert res.exchange_mode == mode and res.loop_mode == (2 if loop == "persist" else 1)
     assert trace == otrace
     assert np.array_equal(tab, o_tab) and np.array_equal(basis, o_basis)
 
 
-def _torchrun(nproc, *args, exchange="p2p"):
-    env = dict(os.environ, B200LP_EXCHANGE=exchange, B200LP_PEER_TIMEOUT_MS="5000")
+def _torchrun(nproc, *args, exchange="p2p", loop="persist"):
+    env = dict(os.environ, B200LP_EXCHANGE=exchange, B200LP_PEER_TIMEOUT_MS="5000", B200LP_LOOP=loop)
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
@@ -59,10 +61,10 @@ def _torchrun(nproc, *args, exchange="p2p"):
 
 
 @needs2
-@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+@pytest.mark.parametrize("exchange,loop", [("p2p", "persist"), ("p2p", "iter"), ("nccl", "iter")])
 @pytest.mark.parametrize("args", [(300, 500), (128, 128, 1, "degenerate"), (128, 128, 0, "degenerate")])
-def test_one_process_per_gpu(args, exchange):
-    out = _torchrun(2, *args, exchange=exchange)
+def test_one_process_per_gpu(args, exchange, loop):
+    out = _torchrun(2, *args, exchange=exchange, loop=loop)
     assert out.returncode == 0 and "SHARDED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
