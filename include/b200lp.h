@@ -99,6 +99,8 @@ typedef struct b200lp_result {
     double  ms_look_push;        /* sharded: scale own candidate row + push to every rank           */
     double  ms_look_peer_wait;   /* sharded: waiting for every rank's candidate                     */
     double  ms_look_row;         /* phase B: pivot row / element, objective row, next entering col  */
+    double  sm_clock_mhz;        /* SM clock seen by the look role (clock64 vs %globaltimer)        */
+    double  ms_look_dbg[8];      /* finer split of the two phases (dev aid; see persist.cuh)        */
 } b200lp_result;
 
 /* ---- one-shot calls: what the `*solver*` backend function uses ------------------------------

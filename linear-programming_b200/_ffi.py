@@ -79,6 +79,8 @@ class Result(ctypes.Structure):
         ("ms_look_push", ctypes.c_double),
         ("ms_look_peer_wait", ctypes.c_double),
         ("ms_look_row", ctypes.c_double),
+        ("sm_clock_mhz", ctypes.c_double),
+        ("ms_look_dbg", ctypes.c_double * 8),
     ]
 
     def as_dict(self):

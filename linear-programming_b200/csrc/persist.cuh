@@ -52,8 +52,12 @@ struct alignas(16) PSync {
     unsigned long long bar[2];           // look-grid barriers (monotonic arrival counts)
     int abort;                           // != 0: some spin timed out; everyone leaves
     int pad;
-    // telemetry, summed over decisions by look CTA 0 (ns of %globaltimer)
+    unsigned long long rebal;            // tile CTAs that reached a re-balancing point (monotonic)
+    // telemetry, summed over decisions by look CTA 0: SM cycles per phase, plus (%globaltimer,
+    // clock64) pairs at both ends of the call to convert them
     unsigned long long look_count, ns_look, ns_wait_done, ns_a, ns_b1, ns_xwait, ns_b2;
+    unsigned long long gt0, clk0, gt1, clk1;
+    unsigned long long dbg[8];           // finer stamps of the lead thread (cycles, summed)
     Cand part[2][kPLookMax];
 };
 
@@ -86,6 +90,8 @@ struct PersistArgs {
     int trace_cap;
     PSync *sync;
     unsigned long long timeout_ns;
+    double *rates;                   // [grid]: measured row units per busy cycle of every CTA (kept across calls)
+    unsigned long long *tile_prof;   // optional [2 * grid]: busy ns and SM id per tile CTA (B200LP_TILE_PROFILE)
     int look_ctas;
     int slot_base;            // ring slot of decision k is (slot_base + k) & 3: the ring keeps turning
                               // across calls, so a rank that is already in the next call never
@@ -96,14 +102,17 @@ struct PersistArgs {
 __device__ __forceinline__ bool spin_ge(const unsigned long long *p, unsigned long long want,
                                         PSync *S, unsigned long long timeout_ns, int code)
 {
+    // deadline on the SM cycle counter (reading %globaltimer costs about a microsecond, which a
+    // latency chain cannot afford): 2 cycles per ns, i.e. between 1x and 2x the nominal timeout
     const volatile unsigned long long *v = p;
     if (*v >= want) return true;
-    const unsigned long long t0 = global_timer_ns();
+    const long long t0 = clock64();
+    const long long budget = (long long)(timeout_ns << 1);
     for (;;) {
         for (int k = 0; k < 32; ++k)
             if (*v >= want) return true;
         if (*reinterpret_cast<volatile int *>(&S->abort)) return false;
-        if (global_timer_ns() - t0 > timeout_ns) {
+        if (clock64() - t0 > budget) {
             atomicCAS(&S->abort, 0, code);
             return false;
         }
@@ -199,7 +208,10 @@ __device__ __noinline__ void persist_look(const PersistArgs &P, const int cta, c
     const int v_begin = cta * chunkV, v_end = min(ldv, v_begin + chunkV);
     const int chunkR = (P.R_local + G - 1) / G;
     const int r_begin = cta * chunkR, r_end = min(P.R_local, r_begin + chunkR);
-    const unsigned long long tl0 = global_timer_ns();
+    if (lead) {
+        S->gt0 = global_timer_ns();
+        S->clk0 = (unsigned long long)clock64();
+    }
 
     // ---- prologue: compact copies of S_0's objective row / RHS column; entering column of pivot 1
     Cand best;
@@ -251,14 +263,14 @@ __device__ __noinline__ void persist_look(const PersistArgs &P, const int cta, c
         const int pslot = (int)((k - 1 + P.slot_base) & (kRing - 1));
         const bool pending = k >= 2;
         const double *src = P.tab[pending ? (int)(k & 1) : 0];       // S_{k-2} (S_0 for k = 1)
-        const unsigned long long t0 = lead ? global_timer_ns() : 0ull;
+        const long long t0 = lead ? clock64() : 0ll;
         if (k >= 3) {
             // S_{k-2} must be complete: every tile CTA has finished update(k-2)
             const unsigned long long want = T * (unsigned long long)((k - 3) / kRing + 1);
             if (!cta_wait_ge(&S->done[(k - 2) & (kRing - 1)], want, S, P.timeout_ns, ST_SPIN_TIMEOUT))
                 return;
         }
-        const unsigned long long t1 = lead ? global_timer_ns() : 0ull;
+        const long long t1 = lead ? clock64() : 0ll;
         const double *colp = P.colring + (int64_t)pslot * P.col_stride;
         const double *prowp = p_prow(P, pslot, w_prev);
         double *col_out = P.colring + (int64_t)slot * P.col_stride;
@@ -306,6 +318,7 @@ __device__ __noinline__ void persist_look(const PersistArgs &P, const int cta, c
                 }
             }
         }
+        const long long ta1 = lead ? clock64() : 0ll;
         __syncthreads();                                           // red[] reuse
         c = cand_block_min<kLookThreads>(c, red);
         if (G > 1) {
@@ -314,8 +327,8 @@ __device__ __noinline__ void persist_look(const PersistArgs &P, const int cta, c
             if (!look_bar(S, 0, bar_n[0], P.timeout_ns)) return;
             c = preduce(S->part[0], G, &s_part);
         }
-        const unsigned long long t2 = lead ? global_timer_ns() : 0ull;
-        unsigned long long t3 = t2, t4 = t2;
+        const long long t2 = lead ? clock64() : 0ll;
+        long long t3 = t2, t4 = t2;
 
         // ---- phase B: candidate row / pivot element, objective-row update, next entering column
         int p = c.row, w = 0;
@@ -412,7 +425,7 @@ __device__ __noinline__ void persist_look(const PersistArgs &P, const int cta, c
                 *reinterpret_cast<volatile unsigned long long *>(
                     P.xchg.peer[tid] + px_flag_off(slot, P.rank, P.ld)) = seq;
             }
-            t3 = lead ? global_timer_ns() : 0ull;
+            t3 = lead ? clock64() : 0ll;
             // B2: ONE wait for every rank's candidate, then the same winner everywhere
             {
                 int ok = 1;
@@ -432,7 +445,7 @@ __device__ __noinline__ void persist_look(const PersistArgs &P, const int cta, c
             }
             __syncthreads();
             p = s_p; w = s_w;
-            t4 = lead ? global_timer_ns() : 0ull;
+            t4 = lead ? clock64() : 0ll;
             if (p >= 0) {
                 const double *prow_k = p_prow(P, slot, w);
                 for (int base = v_begin + tid; base < v_end; base += kPUnits * kLookThreads) {
@@ -470,6 +483,7 @@ __device__ __noinline__ void persist_look(const PersistArgs &P, const int cta, c
             }
             return;
         }
+        const long long tb1 = lead ? clock64() : 0ll;
         __syncthreads();                                           // red[] reuse
         best = cand_block_min<kLookThreads>(best, red);
         if (G > 1) {
@@ -478,6 +492,7 @@ __device__ __noinline__ void persist_look(const PersistArgs &P, const int cta, c
             if (!look_bar(S, 1, bar_n[1], P.timeout_ns)) return;
             best = preduce(S->part[1], G, &s_part);
         }
+        const long long tb2 = lead ? clock64() : 0ll;
         // the scaled pivot row is complete (every look CTA passed the barrier): publish pivot k
         const long long iters_after = iters + 1;
         const bool accept = (best.row >= 0) && (P.rule != 0 || best.q < 0.0 - P.thr_enter);
@@ -502,14 +517,22 @@ __device__ __noinline__ void persist_look(const PersistArgs &P, const int cta, c
             __threadfence();
             *reinterpret_cast<volatile unsigned long long *>(&S->decided) =
                 (unsigned long long)(fin != ST_RUNNING ? k + 1 : k);
-            const unsigned long long t5 = global_timer_ns();
+            const long long t5 = clock64();
             S->look_count += 1;
-            S->ns_wait_done += t1 - t0;
-            S->ns_a += t2 - t1;
-            S->ns_b1 += t3 - t2;
-            S->ns_xwait += t4 - t3;
-            S->ns_b2 += t5 - t4;
-            S->ns_look = t5 - tl0;
+            S->ns_wait_done += (unsigned long long)(t1 - t0);
+            S->ns_a += (unsigned long long)(t2 - t1);
+            S->ns_b1 += (unsigned long long)(t3 - t2);
+            S->ns_xwait += (unsigned long long)(t4 - t3);
+            S->ns_b2 += (unsigned long long)(t5 - t4);
+            S->dbg[0] += (unsigned long long)(ta1 - t1);     // phase A: loads + math + stores issued
+            S->dbg[1] += (unsigned long long)(t2 - ta1);     // phase A: reduce (+ look-grid barrier)
+            S->dbg[2] += (unsigned long long)(tb1 - t4);     // phase B: loads + division + stores issued
+            S->dbg[3] += (unsigned long long)(tb2 - tb1);    // phase B: reduce (+ look-grid barrier)
+            S->dbg[4] += (unsigned long long)(t5 - tb2);     // publication (fence)
+            if (fin != ST_RUNNING) {
+                S->gt1 = global_timer_ns();
+                S->clk1 = (unsigned long long)t5;
+            }
         }
         if (fin != ST_RUNNING) return;
         j_prev = j; p_prev = p; w_prev = w;
@@ -519,48 +542,157 @@ __device__ __noinline__ void persist_look(const PersistArgs &P, const int cta, c
 }
 
 // ---- tile role -----------------------------------------------------------------------------------
-// Chunk of rows [ra, rb) of column tile tx: n-pivot-row part 2 for 256 double2 columns.
-template <int UNROLL, bool STREAM>
-__device__ __forceinline__ void persist_chunk(const double2 *src2, double2 *dst2, const int ldv,
-                                              const int tx, const int ra, const int rb,
-                                              const double *col, const double *prow,
-                                              const int p_local)
+// Work space: the tableau cut into tiles of kPTileRows rows x 256 double2 columns, numbered
+// slab-major (all column tiles of rows 0..15 left to right, then rows 16..31, ...), counted in
+// ROW UNITS (one row of one tile).  Tile CTA c owns the contiguous run [ru0, ru1) of that space
+// for as long as the partition stands, so a thread only ever re-reads cells it wrote itself and
+// the tile role needs no grid barrier between pivots.
+//
+// Equal shares are not equal times: on B200 an SM's share of the memory system depends on where
+// it sits (a fixed-share run measured 377..562 us per CTA on config 3 -- the slowest CTA sets the
+// pace; the per-pivot k_iter launch gets its balance from the hardware CTA scheduler instead).
+// So shares are proportional to each CTA's MEASURED rate (row units per busy cycle): `rates`
+// lives with the shard across calls, and inside a call the tile CTAs re-balance at pivots
+// 4, 16, 64, ... and every 4096 after that -- a barrier among the tile CTAs only (ownership may
+// move only when every write of the previous pivot is visible), off the look CTAs' chain.
+constexpr int kPTileRows = 16;
+
+struct PTile { int tx, ra, rb; };
+
+struct PWork {
+    int tiles_x, R_local;
+    int rl;                         // rows of the last slab (kPTileRows when it is a full one)
+    int RU;                         // row units in the full 16-row slabs: what the shares divide
+};
+
+__device__ __forceinline__ PWork pwork_make(const int ldv, const int R_local)
 {
-    const int cv = tx * kPivotThreads + (int)threadIdx.x;
-    const bool act = cv < ldv;
-    const int lane = threadIdx.x & 31;
-    const double2 pr = act ? ldcg2(prow + 2 * cv) : make_double2(0.0, 0.0);
-    for (int r = ra; r < rb; r += UNROLL) {
-        double cl = 0.0;
-        if (lane < UNROLL && r + lane < rb) cl = __ldcg(col + r + lane);
-        double2 a[UNROLL];
+    PWork q;
+    q.R_local = R_local;
+    q.tiles_x = (ldv + kPivotThreads - 1) / kPivotThreads;
+    const int tiles_y = (R_local + kPTileRows - 1) / kPTileRows;
+    q.rl = R_local - (tiles_y - 1) * kPTileRows;
+    // <= R * C / 512 < 2^31 for anything that fits in HBM
+    q.RU = (q.rl == kPTileRows ? tiles_y : tiles_y - 1) * q.tiles_x * kPTileRows;
+    return q;
+}
+
+// Next piece of this CTA's work: first its run [ru, ru1) of the full slabs, one tile (or the part
+// of a tile inside the run) at a time; then its tiles of the short last slab, which are dealt
+// round-robin (tile tx to CTA tx mod T) -- a run of 1-row pieces would keep one load per thread
+// in flight and make its owner the slowest CTA (config 3 on 8 GPUs: 1 025 rows, last slab = the
+// objective row alone).  false when nothing is left.
+__device__ __forceinline__ bool ptile_next(const PWork &q, int &ru, const int ru1, int &xt,
+                                           const int T, PTile &o)
+{
+    if (ru < ru1) {
+        const int t = ru / kPTileRows, rr = ru % kPTileRows;
+        const int take = min(ru1 - ru, kPTileRows - rr);
+        const int ty = t / q.tiles_x;
+        o.tx = t - ty * q.tiles_x;
+        o.ra = ty * kPTileRows + rr;
+        o.rb = o.ra + take;
+        ru += take;
+        return true;
+    }
+    if (q.rl < kPTileRows && xt < q.tiles_x) {
+        o.tx = xt;
+        o.ra = q.R_local - q.rl;
+        o.rb = q.R_local;
+        xt += T;
+        return true;
+    }
+    return false;
+}
+
+// Share of tile CTA `tcta` under the current rate table.  All threads stage the table in shared
+// memory, thread 0 sums it.  Every CTA evaluates the same expression on the same table in the
+// same order, so neighbouring shares meet exactly.  Ends with a __syncthreads.
+constexpr int kPMaxCtas = 1024;
+__device__ __forceinline__ void ppart_shares(const double *rates, const int G, const int T,
+                                             const int tcta, const int RU, double *s_rates, int *s_ru)
+{
+    for (int c = threadIdx.x; c < T; c += kPivotThreads) s_rates[c] = __ldcg(rates + G + c);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double mean = 0.0;
+        for (int c = 0; c < T; ++c) mean += (s_rates[c] > 0.0) ? s_rates[c] : 0.0;
+        mean = mean > 0.0 ? mean / T : 1.0;
+        const double lo = 0.5 * mean, hi = 2.0 * mean;
+        double tot = 0.0, before = 0.0, upto = 0.0;
+        for (int c = 0; c < T; ++c) {
+            double r = s_rates[c];
+            r = (r > 0.0) ? fmin(fmax(r, lo), hi) : mean;
+            if (c == tcta) before = tot;
+            tot += r;
+            if (c == tcta) upto = tot;
+        }
+        s_ru[0] = (tcta == 0) ? 0 : (int)((double)RU * (before / tot));
+        s_ru[1] = (tcta == T - 1) ? RU : (int)((double)RU * (upto / tot));
+    }
+    __syncthreads();
+}
+
+// n-pivot-row part 2 for rows [ra, rb) (at most kPTileRows) of one column tile.  `cl` is this
+// lane's pivot-column value (lane u holds col[ra + u]), `pr` the thread's slice of the pivot row.
+template <bool STREAM>
+__device__ __forceinline__ void persist_rows(const double2 *src2, double2 *dst2, const int ldv,
+                                             const int cv, const bool act, const int ra, const int rb,
+                                             const double cl, const double2 pr, const int p_local)
+{
+    double2 a[kPTileRows];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u)
-            if (act && r + u < rb) a[u] = ld_tab<STREAM>(src2 + (int64_t)(r + u) * ldv + cv);
+    for (int u = 0; u < kPTileRows; ++u)
+        if (act && ra + u < rb) a[u] = ld_tab<STREAM>(src2 + (int64_t)(ra + u) * ldv + cv);
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const double t = __shfl_sync(0xffffffffu, cl, u);
-            if (act && r + u < rb) {
-                double2 o;
-                o.x = __dsub_rn(a[u].x, __dmul_rn(t, pr.x));
-                o.y = __dsub_rn(a[u].y, __dmul_rn(t, pr.y));
-                if (r + u == p_local) o = pr;
-                st_tab<STREAM>(dst2 + (int64_t)(r + u) * ldv + cv, o);
-            }
+    for (int u = 0; u < kPTileRows; ++u) {
+        const double t = __shfl_sync(0xffffffffu, cl, u);
+        if (act && ra + u < rb) {
+            double2 o;
+            o.x = __dsub_rn(a[u].x, __dmul_rn(t, pr.x));
+            o.y = __dsub_rn(a[u].y, __dmul_rn(t, pr.y));
+            if (ra + u == p_local) o = pr;
+            st_tab<STREAM>(dst2 + (int64_t)(ra + u) * ldv + cv, o);
         }
     }
+}
+
+__device__ __forceinline__ bool prebalance_at(const long long k)
+{
+    if (k < 4) return false;
+    if ((k & 4095) == 0) return true;
+    return k <= 1024 && (k & (k - 1)) == 0 && (__ffsll(k) & 1) == 1;   // 4, 16, 64, 256, 1024
 }
 
 template <int UNROLL, bool STREAM>
 __device__ __forceinline__ void persist_tiles(const PersistArgs &P, const int tcta, const int T)
 {
-    __shared__ int s_status, s_pw[2];
+    __shared__ int s_status, s_pw[2], s_ru[2];
+    __shared__ double s_rates[kPMaxCtas];
     PSync *S = P.sync;
     const int ldv = (int)(P.ld >> 1);
-    const int tiles_x = (ldv + kPivotThreads - 1) / kPivotThreads;
-    // balanced contiguous share of the (column tile, row) space, column-tile major
-    const long long U = (long long)tiles_x * P.R_local;
-    const long long u0 = U * tcta / T, u1 = U * (tcta + 1) / T;
+    const int lane = threadIdx.x & 31;
+    const int G = (int)gridDim.x - T;
+    const PWork q = pwork_make(ldv, P.R_local);
+    // enough work for shares to matter
+    const bool balance = P.rates != nullptr && q.RU >= 64 * T && T <= kPMaxCtas;
+    if (balance) ppart_shares(P.rates, G, T, tcta, q.RU, s_rates, s_ru);
+    if (threadIdx.x == 0) {
+        if (!balance) {
+            s_ru[0] = (int)((long long)q.RU * tcta / T);
+            s_ru[1] = (int)((long long)q.RU * (tcta + 1) / T);
+        }
+        if (P.tile_prof) {
+            unsigned int smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            P.tile_prof[2 * blockIdx.x + 1] = smid;
+        }
+    }
+    __syncthreads();
+    int ru0 = s_ru[0], ru1 = s_ru[1];
+    long long busy = 0, busy_all = 0;        // thread 0: cycles streaming since the last re-balance / in all
+    long long units = 0;
+    unsigned long long rebal_gen = 0;
     for (long long k = 1;; ++k) {
         const int slot = (int)((k + P.slot_base) & (kRing - 1));
         int ok = 1;
@@ -575,23 +707,63 @@ __device__ __forceinline__ void persist_tiles(const PersistArgs &P, const int tc
         if (!__syncthreads_and(ok)) return;
         if (s_status != ST_RUNNING) return;
         const int p = s_pw[0], w = s_pw[1];
+        if (balance && prebalance_at(k)) {
+            // every tile CTA has finished update(k-1) and published its rate before any of them
+            // starts update(k) under the new shares
+            rebal_gen += (unsigned long long)T;
+            if (threadIdx.x == 0) {
+                if (busy > 0 && units > 0) P.rates[blockIdx.x] = (double)units / (double)busy;
+                __threadfence();
+                atomicAdd(&S->rebal, 1ull);
+                ok = spin_ge(&S->rebal, rebal_gen, S, P.timeout_ns, ST_SPIN_TIMEOUT) ? 1 : 0;
+                __threadfence();
+                busy = 0; units = 0;
+            }
+            if (!__syncthreads_and(ok)) return;
+            ppart_shares(P.rates, G, T, tcta, q.RU, s_rates, s_ru);
+            ru0 = s_ru[0]; ru1 = s_ru[1];
+        }
         const int rel = p - P.row0;
         const int p_local = (rel >= 0 && rel < P.m_local) ? rel : -1;
         const double2 *src2 = reinterpret_cast<const double2 *>(P.tab[(k - 1) & 1]);
         double2 *dst2 = reinterpret_cast<double2 *>(P.tab[k & 1]);
         const double *col = P.colring + (int64_t)slot * P.col_stride;
         const double *prow = p_prow(P, slot, w);
-        for (long long u = u0; u < u1;) {
-            const int tx = (int)(u / P.R_local);
-            const int ra = (int)(u - (long long)tx * P.R_local);
-            const int rb = (int)min((long long)P.R_local, ra + (u1 - u));
-            persist_chunk<UNROLL, STREAM>(src2, dst2, ldv, tx, ra, rb, col, prow, p_local);
-            u += rb - ra;
+        const long long tb = (threadIdx.x == 0) ? clock64() : 0ll;
+        // the pivot-row slice and the pivot-column values of the NEXT piece are fetched while
+        // the current one streams
+        int ru = ru0, xt = tcta;
+        PTile nx;
+        nx.tx = 0; nx.ra = 0; nx.rb = 0;
+        bool have = ptile_next(q, ru, ru1, xt, T, nx);
+        double2 pr_n = make_double2(0.0, 0.0);
+        double cl_n = 0.0;
+        if (have) {
+            const int cvn = nx.tx * kPivotThreads + (int)threadIdx.x;
+            if (cvn < ldv) pr_n = ldcg2(prow + 2 * cvn);
+            if (lane < kPTileRows && nx.ra + lane < nx.rb) cl_n = __ldcg(col + nx.ra + lane);
+        }
+        while (have) {
+            const PTile cur = nx;
+            const double2 pr = pr_n;
+            const double cl = cl_n;
+            have = ptile_next(q, ru, ru1, xt, T, nx);
+            if (have) {
+                const int cvn = nx.tx * kPivotThreads + (int)threadIdx.x;
+                pr_n = (cvn < ldv) ? ldcg2(prow + 2 * cvn) : make_double2(0.0, 0.0);
+                cl_n = (lane < kPTileRows && nx.ra + lane < nx.rb) ? __ldcg(col + nx.ra + lane) : 0.0;
+            }
+            const int cv = cur.tx * kPivotThreads + (int)threadIdx.x;
+            persist_rows<STREAM>(src2, dst2, ldv, cv, cv < ldv, cur.ra, cur.rb, cl, pr, p_local);
         }
         __syncthreads();
         if (threadIdx.x == 0) {
+            const long long dt = clock64() - tb;
+            busy += dt; busy_all += dt;
+            units += ru1 - ru0;
             __threadfence();
             atomicAdd(&S->done[k & (kRing - 1)], 1ull);
+            if (P.tile_prof) P.tile_prof[2 * blockIdx.x] = (unsigned long long)busy_all;
         }
     }
 }

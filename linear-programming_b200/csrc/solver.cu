@@ -136,6 +136,8 @@ struct Shard {
     double *objc = nullptr;     // ld doubles: running objective row of the look role
     double *rhsc = nullptr;     // R_local doubles: running RHS column
     PSync *psync = nullptr;
+    double *rates = nullptr;    // per-CTA streaming rates of k_persist's tile role (4096 slots)
+    unsigned long long *tile_prof = nullptr;   // B200LP_TILE_PROFILE only
     int coop = 0;               // cudaDevAttrCooperativeLaunch
     int sm_count = 0;
     int plook_ctas = 1;
@@ -250,6 +252,8 @@ static int alloc_shard(b200lp_solver *s, Shard &sh)
     CU_TRY(cudaMalloc(&sh.objc, sizeof(double) * sh.cap_ld));
     CU_TRY(cudaMalloc(&sh.rhsc, sizeof(double) * sh.cap_rows));
     CU_TRY(cudaMalloc(&sh.psync, sizeof(PSync)));
+    CU_TRY(cudaMalloc(&sh.rates, sizeof(double) * 4096));
+    CU_TRY(cudaMemsetAsync(sh.rates, 0, sizeof(double) * 4096, sh.stream));   // 0 = not measured yet
     CU_TRY(cudaDeviceGetAttribute(&sh.coop, cudaDevAttrCooperativeLaunch, sh.device));
     CU_TRY(cudaDeviceGetAttribute(&sh.sm_count, cudaDevAttrMultiProcessorCount, sh.device));
     std::memset(&sh.xchg, 0, sizeof(sh.xchg));
@@ -292,7 +296,7 @@ static void free_shard(Shard &sh)
     cudaFree(sh.colring); cudaFree(sh.candring); cudaFree(sh.gathring); cudaFree(sh.xbuf);
     cudaFree(sh.ring); cudaFree(sh.report); cudaFree(sh.look_sync);
     cudaFree(sh.partials); cudaFree(sh.st);
-    cudaFree(sh.objc); cudaFree(sh.rhsc); cudaFree(sh.psync);
+    cudaFree(sh.objc); cudaFree(sh.rhsc); cudaFree(sh.psync); cudaFree(sh.rates); cudaFree(sh.tile_prof);
     cudaFree(sh.trace);
     if (sh.h_report) cudaFreeHost(sh.h_report);
     for (int k = 0; k < 4; ++k) {
@@ -810,6 +814,12 @@ static int iterate_persist(b200lp_solver *s, int64_t limit, b200lp_result *out, 
         a.timeout_ns = s->world > 1 ? std::max(s->peer_timeout_ns, s->spin_timeout_ns) : s->spin_timeout_ns;
         a.look_ctas = sh.plook_ctas;
         a.slot_base = (int)(s->ring_base & (kRing - 1));
+        a.rates = getenv("B200LP_NO_BALANCE") ? nullptr : sh.rates;
+        if (getenv("B200LP_TILE_PROFILE")) {
+            if (!sh.tile_prof) CU_TRY(cudaMalloc(&sh.tile_prof, sizeof(unsigned long long) * 2 * 4096));
+            CU_TRY(cudaMemsetAsync(sh.tile_prof, 0, sizeof(unsigned long long) * 2 * 4096, sh.stream));
+            a.tile_prof = sh.tile_prof;
+        }
         const int v = pick_pvariant(s, sh);
 #define X(UN, ST) CU_TRY((launch_persist_t<UN, ST>(sh, a)))
         B200LP_PVARIANTS(X)
@@ -836,6 +846,17 @@ static int iterate_persist(b200lp_solver *s, int64_t limit, b200lp_result *out, 
         if (q.abort && !aborted) aborted = q.abort;
     }
     CU_TRY(cudaSetDevice(s0.device));
+    if (const char *path = getenv("B200LP_TILE_PROFILE")) {
+        if (s0.tile_prof) {                                // dev aid: busy ns and SM id per CTA of the last call
+            std::vector<unsigned long long> tp(2 * 4096);
+            CU_TRY(cudaMemcpy(tp.data(), s0.tile_prof, sizeof(unsigned long long) * tp.size(), cudaMemcpyDeviceToHost));
+            if (FILE *f = std::fopen(path, "w")) {
+                for (int c = 0; c < 4096; ++c)
+                    if (tp[2 * c]) std::fprintf(f, "%d,%llu,%llu\n", c, tp[2 * c + 1], tp[2 * c]);
+                std::fclose(f);
+            }
+        }
+    }
     if (aborted == ST_PEER_TIMEOUT)
         return fail(B200LP_ERR_PEER_TIMEOUT, "iterate", "a peer GPU's candidate never arrived");
     if (aborted)
@@ -861,13 +882,20 @@ static int iterate_persist(b200lp_solver *s, int64_t limit, b200lp_result *out, 
         float ms = 0.f;
         CU_TRY(cudaEventElapsedTime(&ms, s0.ev_begin, s0.ev_end));
         out->ms_solve = ms;
-        out->ms_look_kernel = (double)(ps.ns_wait_done + ps.ns_a + ps.ns_b1 + ps.ns_xwait + ps.ns_b2) * 1e-6;
+        // phase sums are SM cycles; the (%globaltimer, clock64) pairs of the call convert them
+        double ns_per_cycle = 0.52;                        // ~1.92 GHz when the call was too short to tell
+        if (ps.clk1 > ps.clk0 && ps.gt1 > ps.gt0 && ps.gt1 - ps.gt0 > 20000)
+            ns_per_cycle = (double)(ps.gt1 - ps.gt0) / (double)(ps.clk1 - ps.clk0);
+        const double cyc_ms = ns_per_cycle * 1e-6;
+        out->ms_look_kernel = (double)(ps.ns_wait_done + ps.ns_a + ps.ns_b1 + ps.ns_xwait + ps.ns_b2) * cyc_ms;
         out->look_kernel_launches = (int64_t)ps.look_count;
-        out->ms_look_wait = (double)ps.ns_wait_done * 1e-6;
-        out->ms_look_ratio = (double)ps.ns_a * 1e-6;
-        out->ms_look_push = (double)ps.ns_b1 * 1e-6;
-        out->ms_look_peer_wait = (double)ps.ns_xwait * 1e-6;
-        out->ms_look_row = (double)ps.ns_b2 * 1e-6;
+        out->ms_look_wait = (double)ps.ns_wait_done * cyc_ms;
+        out->ms_look_ratio = (double)ps.ns_a * cyc_ms;
+        out->ms_look_push = (double)ps.ns_b1 * cyc_ms;
+        out->ms_look_peer_wait = (double)ps.ns_xwait * cyc_ms;
+        out->ms_look_row = (double)ps.ns_b2 * cyc_ms;
+        out->sm_clock_mhz = 1e3 / ns_per_cycle;
+        for (int q = 0; q < 8; ++q) out->ms_look_dbg[q] = (double)ps.dbg[q] * cyc_ms;
         out->kernel_launches = s->kernel_launches - launches0;
         out->bytes_per_pivot = 16 * (int64_t)s0.R_local * s->C;
         double obj = 0.0;

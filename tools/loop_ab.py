@@ -69,7 +69,9 @@ def main():
                                    us_look_ratio=1e3 * res.ms_look_ratio / n_look,
                                    us_look_push=1e3 * res.ms_look_push / n_look,
                                    us_look_peer_wait=1e3 * res.ms_look_peer_wait / n_look,
-                                   us_look_row=1e3 * res.ms_look_row / n_look)
+                                   us_look_row=1e3 * res.ms_look_row / n_look,
+                                   sm_mhz=res.sm_clock_mhz,
+                                   us_dbg=[round(1e3 * x / n_look, 2) for x in res.ms_look_dbg[:5]])
                     rows.append(row)
                     print(json.dumps(row), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
