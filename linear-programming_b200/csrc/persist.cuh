@@ -46,19 +46,21 @@ constexpr int ST_SPIN_TIMEOUT = -6;      // == B200LP_ERR_INTERNAL
 constexpr int kPLookMax = 16;            // look CTAs of k_persist
 constexpr int kPUnits = 4;               // double2 column units a look thread loads per batch
 
-struct alignas(16) PSync {
-    unsigned long long decided;          // decisions 1..decided are in the ring
-    unsigned long long done[kRing];      // done[k & 3]: tile CTAs that finished update(k), summed over uses
-    unsigned long long bar[2];           // look-grid barriers (monotonic arrival counts)
-    int abort;                           // != 0: some spin timed out; everyone leaves
-    int pad;
-    unsigned long long rebal;            // tile CTAs that reached a re-balancing point (monotonic)
+// Every hot word has its own 128-byte line: `decided` is polled by every tile CTA, done[] takes
+// their atomics, bar[] the look CTAs' -- sharing a line makes each of them wait for the others.
+struct alignas(128) PSync {
+    alignas(128) unsigned long long decided;      // decisions 1..decided are in the ring
+    alignas(128) unsigned long long done[kRing];  // done[k & 3]: tile CTAs that finished update(k), summed over uses
+    alignas(128) unsigned long long bar[2];       // look-grid barriers (monotonic arrival counts)
+    alignas(128) unsigned long long rebal;        // tile CTAs that reached a re-balancing point (monotonic)
+    alignas(128) int abort;                       // != 0: some spin timed out; everyone leaves
     // telemetry, summed over decisions by look CTA 0: SM cycles per phase, plus (%globaltimer,
     // clock64) pairs at both ends of the call to convert them
-    unsigned long long look_count, ns_look, ns_wait_done, ns_a, ns_b1, ns_xwait, ns_b2;
+    alignas(128) unsigned long long look_count;
+    unsigned long long ns_look, ns_wait_done, ns_a, ns_b1, ns_xwait, ns_b2;
     unsigned long long gt0, clk0, gt1, clk1;
-    unsigned long long dbg[8];           // finer stamps of the lead thread (cycles, summed)
-    Cand part[2][kPLookMax];
+    unsigned long long dbg[8];                    // finer stamps of the lead thread (cycles, summed)
+    alignas(128) Cand part[2][kPLookMax];
 };
 
 // Exchange layout of the persistent loop (inside the same peer-mapped buffer k_iter uses):
@@ -119,15 +121,19 @@ __device__ __forceinline__ bool spin_ge(const unsigned long long *p, unsigned lo
     }
 }
 
-// Thread 0 waits, everybody learns the outcome; data published before the flag is visible after.
+// Consumer side of every flag in this file: the producer fences (gpu or system scope) between its
+// data and the flag; the consumer polls the flag with volatile loads and then reads the data ONLY
+// with loads that are served by L2 (ld.cg / volatile), issued after the poll returned (control
+// dependency, and bar.sync for the other threads of the CTA).  A consumer-side __threadfence()
+// would add about a microsecond to every hop of the decision chain (it has to wait for the
+// thread's own outstanding stores) without making anything more visible than L2 already is.
+//
+// Thread 0 waits, everybody learns the outcome.
 __device__ __forceinline__ bool cta_wait_ge(const unsigned long long *p, unsigned long long want,
                                             PSync *S, unsigned long long timeout_ns, int code)
 {
     int ok = 1;
-    if (threadIdx.x == 0) {
-        ok = spin_ge(p, want, S, timeout_ns, code) ? 1 : 0;
-        __threadfence();
-    }
+    if (threadIdx.x == 0) ok = spin_ge(p, want, S, timeout_ns, code) ? 1 : 0;
     return __syncthreads_and(ok) != 0;
 }
 
@@ -141,7 +147,6 @@ __device__ __forceinline__ bool look_bar(PSync *S, int which, unsigned long long
         __threadfence();
         atomicAdd(&S->bar[which], 1ull);
         ok = spin_ge(&S->bar[which], target, S, timeout_ns, ST_SPIN_TIMEOUT) ? 1 : 0;
-        __threadfence();
     }
     return __syncthreads_and(ok) != 0;
 }
@@ -192,7 +197,7 @@ __device__ __forceinline__ void enter_scan(Cand &best, const double o, const int
 }
 
 // ---- look role ---------------------------------------------------------------------------------
-__device__ __noinline__ void persist_look(const PersistArgs &P, const int cta, const int G)
+__device__ __forceinline__ void persist_look(const PersistArgs &P, const int cta, const int G)
 {
     __shared__ Cand red[kLookThreads / 32];
     __shared__ Cand s_part;
@@ -433,7 +438,6 @@ __device__ __noinline__ void persist_look(const PersistArgs &P, const int cta, c
                     const unsigned long long *f = reinterpret_cast<const unsigned long long *>(
                         P.xchg.peer[P.rank] + px_flag_off(slot, tid, P.ld));
                     ok = spin_ge(f, seq, S, P.timeout_ns, ST_PEER_TIMEOUT) ? 1 : 0;
-                    __threadfence_system();
                 }
                 if (!__syncthreads_and(ok)) return;
             }
@@ -698,7 +702,6 @@ __device__ __forceinline__ void persist_tiles(const PersistArgs &P, const int tc
         int ok = 1;
         if (threadIdx.x == 0) {
             ok = spin_ge(&S->decided, (unsigned long long)k, S, P.timeout_ns, ST_SPIN_TIMEOUT) ? 1 : 0;
-            __threadfence();
             const volatile IterState *st = P.ring + slot;
             s_status = st->status;
             s_pw[0] = st->p;
@@ -716,7 +719,6 @@ __device__ __forceinline__ void persist_tiles(const PersistArgs &P, const int tc
                 __threadfence();
                 atomicAdd(&S->rebal, 1ull);
                 ok = spin_ge(&S->rebal, rebal_gen, S, P.timeout_ns, ST_SPIN_TIMEOUT) ? 1 : 0;
-                __threadfence();
                 busy = 0; units = 0;
             }
             if (!__syncthreads_and(ok)) return;

@@ -199,7 +199,10 @@ static void shape_shard(Shard &sh)
     sh.xchg.ld = sh.ld;
     // persistent loop: one look CTA while a row is short (no look-grid barriers at all), else
     // enough that a look thread touches only a few 16-byte units per phase
-    sh.plook_ctas = sh.ld <= 4096 ? 1 : (int)std::min<int64_t>(kPLookMax, std::max<int64_t>(2, (sh.ld + 2047) / 2048));
+    // (measured, profiles/r02_loop_ab_*.json: 3 088-double rows 11.6 us per pivot with one look
+    // CTA, 10.2 us with four; 784-double rows 6.1 us with one, 7.7 us with four)
+    sh.plook_ctas = sh.ld <= 1536 ? 1 : sh.ld <= 8192 ? 4
+                  : (int)std::min<int64_t>(kPLookMax, (sh.ld + 2047) / 2048);
     if (const char *e = getenv("B200LP_LOOK_CTAS")) {
         const int g = atoi(e);
         if (g >= 1 && g <= kPLookMax) sh.plook_ctas = g;
@@ -743,15 +746,26 @@ static int loop_env()
     return 0;
 }
 
-// The persistent loop serves one shard or the peer-mapped exchange; the NCCL fallback (xmode 1)
-// and explicitly requested k_iter tile variants (1..13, the variant sweep) use the per-pivot loop.
+// Which packaging of the loop runs (measured on B200, profiles/r02_loop_ab_*.json):
+//   * tableaus whose two ping-pong buffers stay in the 126 MB L2 are bound by the decision chain
+//     and the launch gap: the persistent cooperative kernel wins (config 2: 10.2 vs 13.4 us per
+//     pivot; m=256, n=512: 6.1 vs 10.8 us);
+//   * anything streamed from HBM is bound by the rank-1 update, and there the hardware CTA
+//     scheduler of a per-pivot launch balances the SMs better than any fixed ownership of tiles
+//     (config 3: 468 vs 545 us; its 1 025-row 8-GPU shard: 62.3 vs 69.1 us): k_iter.
+// B200LP_LOOP=iter|persist and explicit tile variants (1..13 k_iter, 20..23 k_persist) override.
+// The NCCL fallback (xmode 1) always uses the per-pivot loop.
+static constexpr double kPersistMaxBytes = 64e6;
 static bool want_persist(const b200lp_solver *s)
 {
     if (s->xmode == 1 || loop_env() == 1) return false;
-    const int v = s->opts.pivot_variant;
-    if (v >= 1 && v < 20 && loop_env() != 2) return false;
     for (const Shard &sh : s->shards)
         if (!sh.coop) return false;
+    const int v = s->opts.pivot_variant;
+    if (v >= 20 || loop_env() == 2) return true;
+    if (v >= 1) return false;
+    for (const Shard &sh : s->shards)
+        if (8.0 * (double)sh.ld * sh.R_local > kPersistMaxBytes) return false;
     return true;
 }
 
