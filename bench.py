@@ -13,6 +13,7 @@ stream, max over ranks.  `e2e` is the same metric through the reference-facing c
 For N > 1 (torchrun, one process per GPU) the same LP is row-block sharded: strong scaling.
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -180,6 +181,66 @@ def run_reference(args, cfg, workload):
 
 
 # ----------------------------------------------------------------------------------- our arm
+def _sha(arr, dtype):
+    return hashlib.sha256(np.ascontiguousarray(arr, dtype=dtype).tobytes()).hexdigest()
+
+
+def _trace_sha(trace):
+    return _sha(np.asarray(trace, dtype=np.int32).reshape(-1, 2), np.int32)
+
+
+def load_final_fixture(config):
+    """tests/golden/<config>_final.npz: what the ORACLE reaches at the end of the solve (generated
+    by tools/make_full_goldens.py; the GPU box has neither /root/reference nor the minutes a CPU
+    solve takes)."""
+    path = os.path.join(ROOT, "tests", "golden", f"{config}_final.npz")
+    if not os.path.exists(path):
+        return None, path
+    return np.load(path), path
+
+
+def parity_prefix(dev, blk, blk_basis, tab, basis, k_prefix, world, all_min):
+    """Checker leg, OUTSIDE every timed region: K pivots from a fresh upload on the GPU(s) against
+    K pivots of the oracle on the host -- pivot trace, RHS column, objective row and basis, bit
+    for bit.  Each rank checks the rows it owns plus its replica of the objective row."""
+    from oracle import oracle
+    oracle.build()
+    oracle.set_num_threads(max(1, len(os.sched_getaffinity(0)) // max(world, 1)))
+    dev.upload(blk, blk_basis)
+    st, res, trace = dev.iterate(k_prefix)
+    rhs, obj, g_basis = dev.download_solution()
+    o_tab, o_basis = tab.copy(), basis.copy()
+    ost, oit, otrace = oracle.solve(o_tab, o_basis, True, max_iters=k_prefix, parallel=True,
+                                    trace_cap=k_prefix)
+    b, e = dev.row_begin, dev.row_end
+    m = tab.shape[0] - 1
+    if dev.nranks == 1:
+        b, e = 0, m
+    out = {
+        "prefix_pivots": int(oit),
+        "prefix_trace_equal": bool(int(res.iterations) == oit and trace[:oit] == otrace and st == ost),
+        "prefix_rhs_equal": bool(np.array_equal(rhs[:-1], o_tab[b:e, -1]) and rhs[-1] == o_tab[m, -1]),
+        "prefix_obj_row_equal": bool(np.array_equal(obj, o_tab[m])),
+        "prefix_basis_equal": bool(np.array_equal(g_basis, o_basis[b:e])),
+    }
+    del o_tab
+    return {k: (v if k == "prefix_pivots" else all_min(v)) for k, v in out.items()}
+
+
+def parity_final(fixture, status, iters, trace, rhs, obj, g_basis, b, e, all_min):
+    """The e2e solve's end state against the committed oracle fixture, bit for bit."""
+    m = int(fixture["m"])
+    out = {
+        "final_pivots_equal": bool(int(fixture["iterations"]) == iters and int(fixture["status"]) == status),
+        "final_basis_equal": bool(np.array_equal(g_basis, fixture["basis"][b:e])),
+        "final_rhs_equal": bool(np.array_equal(rhs[:-1], fixture["rhs"][b:e]) and rhs[-1] == fixture["rhs"][m]),
+        "final_obj_row_equal": bool(np.array_equal(obj, fixture["obj_row"])),
+        "final_trace_equal": bool(len(trace) == int(fixture["iterations"])
+                                  and _trace_sha(trace) == str(fixture["trace_sha256"])),
+    }
+    return {k: all_min(v) for k, v in out.items()}
+
+
 def run_b200(args, cfg, workload):
     import torch
     from linear_programming_b200 import _ffi, synthetic
@@ -207,34 +268,79 @@ def run_b200(args, cfg, workload):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    m, n = cfg["m"], cfg["n"]
-    R, C = m + 1, n + m + 1
-    # pinned host buffer: the e2e call copies from it; every rank builds the same LP (seeded)
-    host = torch.empty((R, C), dtype=torch.float64, pin_memory=True)
-    tab = host.numpy()
-    _, basis = synthetic.dense_tableau(m, n, degenerate=cfg["degenerate"], out=tab)
+    def all_min(flag):
+        """True only if every rank says so."""
+        if dist is None:
+            return bool(flag)
+        t = torch.tensor([1.0 if flag else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item() > 0.5)
 
-    shard = None
-    if world > 1:
+    def new_uid():
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             uid.copy_(torch.frombuffer(bytearray(_ffi.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
-        shard = (rank, world, bytes(uid.cpu().numpy().tobytes()))
+        return bytes(uid.cpu().numpy().tobytes())
+
+    mps_info = None
+    if args.mps:
+        # f4: a standard LP file instead of the synthetic generator: read_mps -> build_tableau -> solve
+        from linear_programming_b200 import external_formats, simplex
+        t0 = time.perf_counter()
+        with open(args.mps) as f:
+            problem = external_formats.read_mps(f)
+        t1 = time.perf_counter()
+        built = simplex.build_tableau(problem, problem)
+        t2 = time.perf_counter()
+        if isinstance(built, list):
+            raise SystemExit("bench.py --mps: this LP needs phase 1 (>= / = rows); the bench loop times "
+                             "single-phase tableaus -- use linear_programming_b200.solve_problem")
+        src_tab, basis = built.matrix, built.basis_columns
+        is_max = built.instance_problem.type == "max"
+        R, C = src_tab.shape
+        m, n = R - 1, C - R
+        mps_info = {"file": os.path.basename(args.mps), "read_mps_s": t1 - t0, "build_tableau_s": t2 - t1,
+                    "rows": m, "columns": C - 1, "type": built.instance_problem.type}
+        workload = f"MPS {os.path.basename(args.mps)} ({m} rows x {C - 1} columns)"
+        host = torch.empty((R, C), dtype=torch.float64, pin_memory=True)
+        tab = host.numpy()
+        tab[:] = src_tab
+        build_info = None
+    else:
+        is_max = True
+        m, n = cfg["m"], cfg["n"]
+        R, C = m + 1, n + m + 1
+        # pinned host buffer: the e2e call copies from it; every rank builds the same LP (seeded).
+        # f2: the fp64 tableau is written straight into it (no boxed intermediate, no second pass)
+        host = torch.empty((R, C), dtype=torch.float64, pin_memory=True)
+        tab = host.numpy()
+        A, bvec, cvec = synthetic.dense_lp(m, n, degenerate=cfg["degenerate"])
+        t0 = time.perf_counter()
+        _, basis = synthetic.tableau_from_lp(A, bvec, cvec, out=tab)
+        t_build = time.perf_counter() - t0
+        del A
+        build_info = {"what": "build-tableau's fill (src/simplex.lisp:214-287) written as fp64 straight "
+                              "into the pinned upload buffer", "seconds": t_build,
+                      "bytes": 8 * R * C, "gb_per_s": 8e-9 * R * C / t_build}
+
+    shard = (rank, world, new_uid()) if world > 1 else None
     # `--gpus N` without torchrun: one process drives N GPUs (the library shards in-process)
     inproc = args.gpus if (world == 1 and args.gpus > 1) else 1
     if inproc > torch.cuda.device_count():
         raise SystemExit(f"bench.py: --gpus {inproc} but {torch.cuda.device_count()} visible")
     devices = list(range(inproc)) if inproc > 1 else [local_rank]
+    trace_cap = 1 << 15
     opts = _ffi.make_opts(devices=devices, time_kernels=True, pivot_variant=args.variant,
-                          poll_interval=args.poll)
-    dev = _ffi.DeviceTableau(R, C, True, opts, shard=shard)
+                          poll_interval=args.poll, trace_capacity=trace_cap)
+    dev = _ffi.DeviceTableau(R, C, is_max, opts, shard=shard)
     if shard is None:
         blk, blk_basis = tab, basis
+        row_b, row_e = 0, m
     else:
-        b, e = dev.row_begin, dev.row_end
-        blk = np.ascontiguousarray(np.vstack([tab[b:e], tab[m:m + 1]]))
-        blk_basis = np.ascontiguousarray(basis[b:e])
+        row_b, row_e = dev.row_begin, dev.row_end
+        blk = np.ascontiguousarray(np.vstack([tab[row_b:row_e], tab[m:m + 1]]))
+        blk_basis = np.ascontiguousarray(basis[row_b:row_e])
 
     # ---- device-resident K steps ---------------------------------------------------------
     # Timed region: K iterations enqueued back to back (no host work, no events between launches),
@@ -254,14 +360,18 @@ def run_b200(args, cfg, workload):
     ms_total = max_over_ranks(res.ms_solve)
     launches = int(res.kernel_launches)
     bytes_per_launch = int(res.bytes_per_pivot)
+    loop_mode = int(res.loop_mode)
     value = steps_done / (ms_total / 1e3)
     ms_look = max_over_ranks(res.ms_look_kernel / max(res.look_kernel_launches, 1))
-    dev.set_time_kernels(True)
-    barrier()
-    st_b, res_b, _ = dev.iterate(args.steps)
-    ms_pivot_isolated = max_over_ranks(res_b.ms_pivot_kernel / max(res_b.pivot_kernel_launches, 1))
-    ms_exch = max_over_ranks(res_b.ms_exchange / max(res_b.look_kernel_launches, 1))
-    dev.set_time_kernels(False)
+    ms_pivot_isolated = None
+    ms_exch = 0.0
+    if loop_mode == 1:
+        dev.set_time_kernels(True)
+        barrier()
+        st_b, res_b, _ = dev.iterate(args.steps)
+        ms_pivot_isolated = max_over_ranks(res_b.ms_pivot_kernel / max(res_b.pivot_kernel_launches, 1))
+        ms_exch = max_over_ranks(res_b.ms_exchange / max(res_b.look_kernel_launches, 1))
+        dev.set_time_kernels(False)
     clocks = sampler.stop() if rank == 0 else None   # 20 ms samples: warm-up, timed and isolated passes
     if clocks is not None:
         clocks["window"] = "warm-up + timed region + per-launch pass (same kernel throughout)"
@@ -269,40 +379,95 @@ def run_b200(args, cfg, workload):
     # (inter-launch gaps included, so this can only under-state the kernel)
     ms_pivot = ms_total / max(steps_done, 1)
 
+    # ---- parity, part 1 (checker leg, untimed): a prefix against the oracle on the host --------
+    parity = None
+    if not args.no_parity and is_max:
+        parity = parity_prefix(dev, blk, blk_basis, tab, basis, args.parity_prefix, world * inproc, all_min)
+
     # ---- e2e: through the reference-facing call, host buffers in, solution out -----------
     e2e = None
+    fixture, fixture_path = (None, None) if args.mps else load_final_fixture(args.config)
     if not args.no_e2e:
         barrier()
         t0 = time.perf_counter()
         if shard is None:
             eb = basis.copy()
-            st2, r2, _ = _ffi.solve(tab, eb, True, _ffi.make_opts(devices=devices,
-                                                                   pivot_variant=args.variant,
-                                                                   poll_interval=args.poll,
-                                                                   max_iters=args.e2e_max_iters))
+            st2, r2, e_trace = _ffi.solve(tab, eb, is_max, _ffi.make_opts(
+                devices=devices, pivot_variant=args.variant, poll_interval=args.poll,
+                max_iters=args.e2e_max_iters, trace_capacity=trace_cap))
             iters = int(r2.iterations)
             h2d, d2h = int(r2.h2d_bytes), int(r2.d2h_bytes)
             breakdown = {"ms_h2d": r2.ms_h2d, "ms_solve": r2.ms_solve, "ms_d2h": r2.ms_d2h,
                          "ms_total_in_call": r2.ms_total}
+            e_rhs, e_obj, e_basis = tab[:, C - 1].copy(), tab[m].copy(), eb
         else:
             breakdown = None
             dev.upload(blk, blk_basis)
-            st2, r2, _ = dev.iterate(args.e2e_max_iters)
-            dev.download_solution()
+            st2, r2, e_trace = dev.iterate(args.e2e_max_iters)
+            e_rhs, e_obj, e_basis = dev.download_solution()
             iters = int(r2.iterations)
             h2d = blk.nbytes + blk_basis.nbytes
-            d2h = 8 * (blk.shape[0] + C) + 4 * blk_basis.size
+            d2h = 8 * (blk.shape[0] + C) + 4 * blk_basis.size + 8 * min(iters, trace_cap)
         torch.cuda.synchronize()
         wall = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": iters / wall, "unit": UNIT,
                "h2d_bytes_per_step": h2d / max(iters, 1), "d2h_bytes_per_step": d2h / max(iters, 1),
                "pivots": iters, "wall_s": wall, "status": int(st2), "breakdown": breakdown,
+               "objective": float(r2.objective),
+               "basis_sha256_local_rows": _sha(e_basis, np.int32),
+               "trace_sha256": _trace_sha(e_trace) if iters <= trace_cap else None,
                "what": "one solve call: pinned host tableau H2D + all pivots + solution D2H"}
+        # ---- parity, part 2: the end state against the committed full-solve fixture ------
+        if parity is not None and args.e2e_max_iters == 0:
+            if fixture is not None:
+                parity.update(parity_final(fixture, int(st2), iters, e_trace, e_rhs, e_obj, e_basis,
+                                           row_b, row_e, all_min))
+                parity["final_fixture"] = os.path.relpath(fixture_path, ROOT)
+                parity["fixture_objective"] = float(fixture["objective"])
+            else:
+                parity["final_fixture"] = None
+            parity["objective"] = float(r2.objective)
+    if parity is not None:
+        parity["checker"] = ("oracle/simplex_oracle.c on the host for the prefix; committed oracle "
+                             "end state (tools/make_full_goldens.py) for the full solve; bit-exact compares")
     dev.close()
+
+    # ---- BASELINE config 4 (the one the north star names for 2/4/8 GPUs), same row-block sharding
+    cfg4 = None
+    if args.with_cfg4 and not args.mps and args.config == "cfg3":
+        m4, n4 = CONFIGS["cfg4"]["m"], CONFIGS["cfg4"]["n"]
+        R4, C4 = m4 + 1, n4 + m4 + 1
+        tc0 = time.perf_counter()
+        if world > 1:
+            b4, e4 = _ffi.partition(m4, world, rank)
+            blk4, basis4 = synthetic.dense_block(m4, n4, b4, e4)
+            dev4 = _ffi.DeviceTableau(R4, C4, True, _ffi.make_opts(devices=[local_rank]),
+                                      shard=(rank, world, new_uid()))
+        else:
+            blk4, basis4 = synthetic.dense_block(m4, n4, 0, m4)
+            dev4 = _ffi.DeviceTableau(R4, C4, True, _ffi.make_opts(devices=devices))
+        t_gen = time.perf_counter() - tc0
+        dev4.upload(blk4, basis4)
+        del blk4
+        dev4.iterate(args.warmup)
+        barrier()
+        st4, res4, _ = dev4.iterate(args.cfg4_steps)
+        barrier()
+        ms4 = max_over_ranks(res4.ms_solve)
+        it4 = int(res4.iterations)
+        obj4 = float(res4.objective)
+        dev4.close()
+        peak4, _ = load_peak()
+        gbs4 = int(res4.bytes_per_pivot) * it4 / (ms4 * 1e-3) / 1e9
+        cfg4 = {"workload": "dense fp64 LP m=16384 n=32768 (BASELINE cfg4), seed 1234",
+                "value": it4 / (ms4 / 1e3), "unit": UNIT, "steps": it4, "ms_per_step": ms4 / max(it4, 1),
+                "gbs_per_gpu": gbs4, "frac_of_measured_peak_per_gpu": gbs4 / peak4,
+                "objective_after_steps": obj4, "setup_s": t_gen,
+                "what": "same timed-region method as the headline, tableau resident in HBM"}
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores --------------
     cpu = None
-    if rank == 0 and world == 1 and inproc == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and inproc == 1 and not args.no_cpu_baseline and not args.mps:
         from oracle import oracle
         oracle.build()
         oracle.set_num_threads(len(os.sched_getaffinity(0)))
@@ -337,34 +502,43 @@ def run_b200(args, cfg, workload):
     if rank == 0:
         peak, peak_src = load_peak()
         achieved = bytes_per_launch / (ms_pivot * 1e-3) / 1e9
+        ngpu = world * inproc
+        kernel = {1: "k_iter (rank-1 update tiles + lookahead CTAs), one launch per pivot",
+                  2: "k_persist (one cooperative kernel per call: look CTAs + tile CTAs)"}[loop_mode]
+        if int(res.exchange_mode) == 1:
+            kernel = "k_update (NCCL fallback: k_look + all-gather + k_update)"
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world * inproc,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ngpu,
             "steps": steps_done,
             "warmup": args.warmup, "ms_per_step": ms_total / max(steps_done, 1),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": workload, "m": m, "n": n, "R": R, "C": C,
-                       "tableau_bytes": 8 * R * C, "sharding": f"row-block x{world * inproc}" + (" (one process)" if inproc > 1 else ""),
-                       "exchange": {0: "none (one shard)", 1: "NCCL all-gather between kernels",
-                                    2: "peer-mapped buffers, inside the iteration kernel"}[
-                                        int(res.exchange_mode)],
-                       "l2": "tableau >> 126 MB L2, no flush needed" if 8 * R * C // (world * inproc) > 3e8
-                             else "tableau per GPU may be L2 resident",
-                       "status_after_steps": int(st)},
+            "data": "synthetic" if not args.mps else "file",
+            "config": {"workload": workload, "m": m, "n": n, "R": R, "C": C},
+            "run": {"tableau_bytes": 8 * R * C,
+                    "sharding": f"row-block x{ngpu}" + (" (one process)" if inproc > 1 else ""),
+                    "exchange": {0: "none (one shard)", 1: "NCCL all-gather between kernels",
+                                 2: "peer-mapped buffers, inside the iteration kernel"}[
+                                     int(res.exchange_mode)],
+                    "loop": {1: "one k_iter launch per pivot (PDL)", 2: "persistent cooperative kernel"}[loop_mode],
+                    "l2": "tableau >> 126 MB L2, no flush needed" if 8 * R * C // ngpu > 3e8
+                          else "tableau per GPU may be L2 resident",
+                    "status_after_steps": int(st)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
-                         "traffic": load_traffic(workload) if world * inproc == 1 else None,
-                         "kernel": "k_iter (rank-1 update tiles + lookahead CTAs)" if int(res.exchange_mode) != 1 else "k_update", "bytes_per_launch": bytes_per_launch,
+                         "traffic": load_traffic(workload) if ngpu == 1 else None,
+                         "kernel": kernel, "bytes_per_launch": bytes_per_launch,
                          "ms_per_launch": ms_pivot,
                          "ms_per_launch_isolated": ms_pivot_isolated,
-                         "how": "achieved = bytes_per_launch / (CUDA-event time of the K back-to-back "
-                                "launches / K); isolated = events around each launch in a second pass",
+                         "how": "achieved = algorithmic bytes per pivot (16*R_local*C) / (CUDA-event time of "
+                                "the K back-to-back pivots / K); isolated = events around each launch in a "
+                                "second pass (per-pivot loop only)",
                          "peak_source": peak_src,
                          "frac_of_nominal_8TBps": achieved / 8000.0},
             "overlapped": {"what": "lookahead CTAs (entering column, ratio test, pivot-row scaling and, "
                                    "sharded, the candidate exchange) run inside the same launch, "
                                    "concurrently with the update tiles",
                            "ms_look": ms_look, "ms_exchange_nccl_fallback": ms_exch},
+            "parity": parity, "cfg4": cfg4, "build_tableau": build_info, "mps": mps_info,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
@@ -386,6 +560,12 @@ def main():
     ap.add_argument("--e2e-max-iters", type=int, default=0, help="0 = solve to optimality")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle / fixture checker legs")
+    ap.add_argument("--parity-prefix", type=int, default=10, help="pivots compared with the oracle")
+    ap.add_argument("--no-cfg4", dest="with_cfg4", action="store_false",
+                    help="skip the BASELINE config 4 sub-record")
+    ap.add_argument("--cfg4-steps", type=int, default=200)
+    ap.add_argument("--mps", default=None, help="bench an LP read from an MPS file (single-phase LPs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfg = CONFIGS[args.config]

@@ -51,5 +51,32 @@ def dense_tableau(m, n, seed=1234, degenerate=False, out=None, zero_frac=0.5):
     return tableau_from_lp(A, b, c, out=out)
 
 
+def dense_block(m, n, row_begin, row_end, seed=1234, out=None):
+    """Rows [row_begin, row_end) of dense_tableau(m, n, seed) plus its objective row, WITHOUT
+    materialising the other rows: the (row_end - row_begin + 1) x (n + m + 1) block a rank of a
+    row-block sharded solve uploads, and its slice of the slack basis.  PCG64 is advanced past
+    the rows that are skipped (one 64-bit draw per double), so the values are bit-identical to
+    the full generator's (tests/test_host_frontend.py)."""
+    rng = np.random.default_rng(seed)
+    rows = row_end - row_begin
+    C = n + m + 1
+    blk = out if out is not None else np.zeros((rows + 1, C))
+    if out is not None:
+        blk[:] = 0.0
+    rng.bit_generator.advance(row_begin * n)
+    step = max(1, (1 << 24) // max(n, 1))                  # ~128 MB of draws at a time
+    for r0 in range(0, rows, step):
+        r1 = min(rows, r0 + step)
+        blk[r0:r1, :n] = rng.random((r1 - r0, n))
+    rng.bit_generator.advance((m - row_end) * n)
+    b = rng.uniform(n / 8.0, 3.0 * n / 8.0, m)
+    c = rng.random(n)
+    blk[np.arange(rows), n + row_begin + np.arange(rows)] = 1.0
+    blk[:rows, C - 1] = b[row_begin:row_end]
+    blk[rows, :n] = -c
+    basis = np.arange(n + row_begin, n + row_end, dtype=np.int32)
+    return blk, basis
+
+
 README_LP = dict(A=np.array([[2.0, 1.0, 0.0], [0.0, 1.0, 1.0]]), b=np.array([8.0, 7.0]),
                  c=np.array([1.0, 4.0, 3.0]))  # README.md:30-62 -> obj 57/2, x=(1/2, 7, 0)

@@ -223,3 +223,15 @@ def test_random_integer_problems_agree_with_a_milp_solver(oracle_device):
     import random_problems
     for seed in range(80):
         random_problems.check_integer(seed)
+
+
+def test_dense_block_equals_the_rows_of_the_full_generator():
+    """synthetic.dense_block (what a rank of a sharded bench uploads) skips the other ranks' rows by
+    advancing PCG64; the block must be bit-identical to the same rows of dense_tableau."""
+    import numpy as np
+    from linear_programming_b200 import synthetic
+    full, basis = synthetic.dense_tableau(37, 53)
+    for lo, hi in [(0, 37), (5, 20), (30, 37), (0, 1)]:
+        blk, bb = synthetic.dense_block(37, 53, lo, hi)
+        assert np.array_equal(blk[:-1], full[lo:hi]) and np.array_equal(blk[-1], full[-1])
+        assert np.array_equal(bb, basis[lo:hi])
