@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200LP_VERSION 102 /* 0.1.2 */
+#define B200LP_VERSION 200 /* 0.2.0 */
 #define B200LP_MAX_DEVICES 8
 
 /* ---- status codes --------------------------------------------------------------------------
@@ -39,7 +39,10 @@ enum {
     B200LP_UNBOUNDED = 1,         /* src/simplex.lisp:458-459 -> unbounded-problem-error         */
     B200LP_INFEASIBLE = 2,        /* src/simplex.lisp:405-407 -> infeasible-problem-error        */
     B200LP_ITERATION_LIMIT = 3,   /* build extension (reference has no cap): opts.max_iters hit  */
-    B200LP_ARTIFICIAL_STUCK = 4,  /* src/simplex.lisp:423-424, 432-433 (plain `error`)           */
+    B200LP_ARTIFICIAL_STUCK = 4,  /* src/simplex.lisp:432-433 (plain `error`): an artificial variable
+                                     is still basic and no column can replace it (B200LP_FEAS_REFERENCE only) */
+    B200LP_ARTIFICIAL_NONZERO = 5,/* src/simplex.lisp:423-424 (plain `error`): an artificial variable
+                                     is still basic at a non-zero level                           */
     B200LP_ERR_INVALID_ARG = -1,
     B200LP_ERR_CUDA = -2,
     B200LP_ERR_NCCL = -3,
@@ -48,6 +51,17 @@ enum {
     B200LP_ERR_INTERNAL = -6,
     B200LP_ERR_PEER_TIMEOUT = -7  /* sharded: a peer GPU's candidate row never arrived            */
 };
+
+/* How the two-phase transition (src/simplex.lisp:402-434) judges "zero".  The reference keeps
+ * exact rationals exact, so its ABSOLUTE tolerance tol*eps (:405-406) and its exact `/= 0`
+ * tests (:423, :427) only ever meet floating-point residue when the user's input is floating
+ * point.  This backend coerces everything to fp64, so by default (B200LP_FEAS_SCALED) it scales
+ * the tolerance by s = max(1, |initial phase-1 objective|): infeasible iff |obj| > tol*eps*s; a
+ * basic artificial must have |RHS| <= tol*eps*s; it is replaced by the non-basic column with the
+ * largest |entry| > (tol/2)*eps (first index on ties); a row with no such column is redundant and
+ * keeps its artificial at level zero (no error).  B200LP_FEAS_REFERENCE applies the reference's
+ * tests literally.  oracle/simplex_oracle.c implements both, and the parity tests cover both. */
+enum { B200LP_FEAS_SCALED = 0, B200LP_FEAS_REFERENCE = 1 };
 
 enum { B200LP_RULE_REFERENCE = 0, /* Dantzig, first index on ties: src/simplex.lisp:362-389      */
        B200LP_RULE_BLAND = 1 };   /* build extension: anti-cycling                 */
@@ -64,7 +78,8 @@ typedef struct b200lp_opts {
     int32_t poll_interval;       /* pivots enqueued between host polls of the status word; 0 = auto */
     int32_t time_kernels;        /* record CUDA events around every pivot-update launch             */
     int32_t pivot_variant;       /* tuning knob for the rank-1 update kernel; 0 = default           */
-    int32_t reserved[6];
+    int32_t feas_mode;           /* B200LP_FEAS_* (two-phase calls)                                 */
+    int32_t reserved[5];
 } b200lp_opts;
 
 /* ---- result / telemetry -------------------------------------------------------------------- */
@@ -101,6 +116,7 @@ typedef struct b200lp_result {
     double  ms_look_row;         /* phase B: pivot row / element, objective row, next entering col  */
     double  sm_clock_mhz;        /* SM clock seen by the look role (clock64 vs %globaltimer)        */
     double  ms_look_dbg[8];      /* finer split of the two phases (dev aid; see persist.cuh)        */
+    int64_t redundant_rows;      /* two-phase, B200LP_FEAS_SCALED: rows left with a zero-level artificial */
 } b200lp_result;
 
 /* ---- one-shot calls: what the `*solver*` backend function uses ------------------------------
@@ -178,6 +194,9 @@ void b200lp_shutdown(void);
 /* ---- misc ----------------------------------------------------------------------------------- */
 const char *b200lp_strerror(int code);
 int b200lp_version(void);
+/* sizeof(b200lp_opts), sizeof(b200lp_result): a binding that declares the structs by hand (the
+ * CFFI shim, ctypes) asserts its own sizes against these when it loads */
+void b200lp_abi_sizes(int64_t *opts_size, int64_t *result_size);
 int b200lp_device_count(void);            /* CUDA devices visible; 0 when there is none          */
 const char *b200lp_last_error(void);      /* text of the last CUDA/NCCL failure on this thread   */
 /* thresholds actually used, for parity tests: (tol/8)eps, (tol/2)eps, tol*eps with

@@ -14,7 +14,8 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "b200lp.h")
 
 MAX_DEVICES = 8
 
-OK, UNBOUNDED, INFEASIBLE, ITERATION_LIMIT, ARTIFICIAL_STUCK = 0, 1, 2, 3, 4
+OK, UNBOUNDED, INFEASIBLE, ITERATION_LIMIT, ARTIFICIAL_STUCK, ARTIFICIAL_NONZERO = 0, 1, 2, 3, 4, 5
+FEAS_SCALED, FEAS_REFERENCE = 0, 1
 ERR_INVALID_ARG, ERR_CUDA, ERR_NCCL, ERR_NO_DEVICE, ERR_OUT_OF_MEMORY, ERR_INTERNAL = \
     -1, -2, -3, -4, -5, -6
 ERR_PEER_TIMEOUT = -7
@@ -45,7 +46,8 @@ class Opts(ctypes.Structure):
         ("poll_interval", ctypes.c_int32),
         ("time_kernels", ctypes.c_int32),
         ("pivot_variant", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 6),
+        ("feas_mode", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 5),
     ]
 
 
@@ -81,6 +83,7 @@ class Result(ctypes.Structure):
         ("ms_look_row", ctypes.c_double),
         ("sm_clock_mhz", ctypes.c_double),
         ("ms_look_dbg", ctypes.c_double * 8),
+        ("redundant_rows", ctypes.c_int64),
     ]
 
     def as_dict(self):
@@ -121,6 +124,7 @@ SIGNATURES = {
     "b200lp_shutdown": (None, []),
     "b200lp_strerror": (ctypes.c_char_p, [ctypes.c_int]),
     "b200lp_version": (ctypes.c_int, []),
+    "b200lp_abi_sizes": (None, [_lp, _lp]),
     "b200lp_device_count": (ctypes.c_int, []),
     "b200lp_last_error": (ctypes.c_char_p, []),
     "b200lp_thresholds": (None, [ctypes.c_double, _dp, _dp, _dp]),
@@ -145,6 +149,12 @@ def lib():
                 raise B200LibraryError(f"{LIB_PATH} does not export {name}") from exc
             fn.restype = res
             fn.argtypes = args
+        so, sr = ctypes.c_int64(), ctypes.c_int64()
+        L.b200lp_abi_sizes(ctypes.byref(so), ctypes.byref(sr))
+        if (so.value, sr.value) != (ctypes.sizeof(Opts), ctypes.sizeof(Result)):
+            raise B200LibraryError(
+                f"{LIB_PATH}: struct sizes {(so.value, sr.value)} != this binding's "
+                f"{(ctypes.sizeof(Opts), ctypes.sizeof(Result))} -- rebuild the library")
         _lib = L
     return _lib
 
@@ -165,7 +175,7 @@ def _check(code, where):
 
 def make_opts(fp_tolerance=1024.0, pivot_rule=RULE_REFERENCE, max_iters=0, devices=None,
               writeback_full=False, trace_capacity=0, poll_interval=0, time_kernels=False,
-              pivot_variant=0):
+              pivot_variant=0, feas_mode=FEAS_SCALED):
     o = Opts()
     o.fp_tolerance_factor = float(fp_tolerance)
     o.pivot_rule = int(pivot_rule)
@@ -175,6 +185,7 @@ def make_opts(fp_tolerance=1024.0, pivot_rule=RULE_REFERENCE, max_iters=0, devic
     o.poll_interval = int(poll_interval)
     o.time_kernels = int(bool(time_kernels))
     o.pivot_variant = int(pivot_variant)
+    o.feas_mode = int(feas_mode)
     if devices is None:
         o.ndev = 0
     else:

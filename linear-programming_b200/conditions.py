@@ -71,4 +71,6 @@ def raise_for_status(status):
         raise SolverError("iteration limit reached")
     if status == 4:
         raise SolverError("Artificial variable still in basis and cannot be replaced")
+    if status == 5:
+        raise SolverError("Artificial variable still non-zero")
     raise SolverError(f"b200lp status {status}")

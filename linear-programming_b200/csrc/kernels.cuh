@@ -1009,10 +1009,11 @@ __global__ void k_copy_art_to_main(const double *__restrict__ art, int64_t ld_ar
 // snapshot taken here), obj[c] -= scale_i * main[i,c] when scale_i /= 0.  One thread per column
 // keeps the row order, hence the rounding sequence, of the reference.
 __global__ void k_reprice_scales(const double *__restrict__ obj, const int32_t *__restrict__ basis,
-                                 int m, double *__restrict__ scales)
+                                 int m, int nv, double *__restrict__ scales)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < m) scales[i] = obj[basis[i]];
+    // a redundant row's zero-level artificial (B200LP_FEAS_SCALED) has no column here: nothing to price
+    if (i < m) scales[i] = basis[i] < nv ? obj[basis[i]] : 0.0;
 }
 
 __global__ void k_reprice(double *__restrict__ mtab, int64_t ld, int m, int nv,
@@ -1042,6 +1043,26 @@ __global__ void k_first_nonzero_nonbasic(const double *__restrict__ row, int nv,
     atomicMin(&best, mine);
     __syncthreads();
     if (threadIdx.x == 0) *out = (best == 0x7fffffff) ? -1 : best;
+}
+
+// B200LP_FEAS_SCALED's replacement rule: the non-basic column j < nv with the largest |entry|
+// above `thr` (first index on ties); result -1 when none.  Single CTA.
+__global__ void k_largest_nonbasic(const double *__restrict__ row, int nv,
+                                   const unsigned char *__restrict__ is_basic, double thr, int *out)
+{
+    __shared__ Cand red[1024 / 32];
+    Cand best;
+    best.q = 0.0; best.key = 0; best.row = -1;
+    for (int c = threadIdx.x; c < nv; c += blockDim.x) {
+        const double a = fabs(row[c]);
+        if (a > thr && !is_basic[c]) {
+            Cand d;
+            d.q = -a; d.key = c; d.row = c;               // (-|a|, index) minimum == largest, first index
+            best = cand_min(best, d);
+        }
+    }
+    best = cand_block_min<1024>(best, red);
+    if (threadIdx.x == 0) *out = best.row;
 }
 
 } // namespace b200lp

@@ -1444,6 +1444,12 @@ void b200lp_partition(int64_t m, int32_t nranks, int32_t rank, int64_t *row_begi
 
 int b200lp_version(void) { return B200LP_VERSION; }
 
+void b200lp_abi_sizes(int64_t *opts_size, int64_t *result_size)
+{
+    if (opts_size) *opts_size = (int64_t)sizeof(b200lp_opts);
+    if (result_size) *result_size = (int64_t)sizeof(b200lp_result);
+}
+
 void b200lp_shutdown(void)
 {
     std::vector<b200lp_solver *> idle;
@@ -1471,6 +1477,7 @@ const char *b200lp_strerror(int code)
     case B200LP_INFEASIBLE: return "Problem has no feasible region";
     case B200LP_ITERATION_LIMIT: return "iteration limit reached";
     case B200LP_ARTIFICIAL_STUCK: return "Artificial variable still in basis and cannot be replaced";
+    case B200LP_ARTIFICIAL_NONZERO: return "Artificial variable still non-zero";
     case B200LP_ERR_INVALID_ARG: return "invalid argument";
     case B200LP_ERR_CUDA: return "CUDA error";
     case B200LP_ERR_NCCL: return "NCCL error";
@@ -1756,7 +1763,7 @@ int b200lp_solve_two_phase(const b200lp_opts *opts, double *art_tab, int64_t C_a
     b200lp_result r1, r2;
     std::memset(&r1, 0, sizeof(r1));
     std::memset(&r2, 0, sizeof(r2));
-    int64_t cleanup = 0;
+    int64_t cleanup = 0, redundant = 0;
     int status = B200LP_OK;
     unsigned char *d_is_basic = nullptr;
     int *d_newcol = nullptr;
@@ -1771,6 +1778,7 @@ int b200lp_solve_two_phase(const b200lp_opts *opts, double *art_tab, int64_t C_a
             out->status = st;
             out->iterations_phase1 = r1.iterations;
             out->iterations_cleanup = cleanup;
+            out->redundant_rows = redundant;
             out->ms_solve = r1.ms_solve + r2.ms_solve;
             out->kernel_launches = r1.kernel_launches + r2.kernel_launches;
             out->h2d_bytes = (int64_t)sizeof(double) * R * (C + C_art);
@@ -1779,6 +1787,11 @@ int b200lp_solve_two_phase(const b200lp_opts *opts, double *art_tab, int64_t C_a
         return st;
     };
     const int64_t m = R - 1, nv = C - 1, art_nv = C_art - 1;
+    // "zero" in the transition: the reference's absolute tests, or (default) scaled by the size of
+    // the numbers that cancel in the phase-1 objective -- see B200LP_FEAS_* in the header
+    const bool ref_feas = opts && opts->feas_mode == B200LP_FEAS_REFERENCE;
+    const double obj0 = art_tab[(R - 1) * ld_art + art_nv];
+    const double feas_scale = ref_feas ? 1.0 : std::fmax(1.0, std::fabs(obj0));
     int rc = acquire(opts, R, C_art, /*is_max=*/0, &art);         // phase 1 is a `min` problem
     if (rc) return finish(rc);
     rc = acquire(opts, R, C, is_max, &mn);
@@ -1789,7 +1802,8 @@ int b200lp_solve_two_phase(const b200lp_opts *opts, double *art_tab, int64_t C_a
     status = b200lp_iterate(art, 0, &r1, nullptr, nullptr);
     if (status != B200LP_OK) return finish(status);
     // (unless (fp= 0 obj tol) (error 'infeasible-problem-error))  :405-407
-    if (!(std::fabs(0.0 - r1.objective) <= art->thr_feas)) return finish(B200LP_INFEASIBLE);
+    const double thr_feas = art->thr_feas * feas_scale;
+    if (!(std::fabs(0.0 - r1.objective) <= thr_feas)) return finish(B200LP_INFEASIBLE);
 
     Shard &as = art->shards[0];
     Shard &ms = mn->shards[0];
@@ -1815,16 +1829,25 @@ int b200lp_solve_two_phase(const b200lp_opts *opts, double *art_tab, int64_t C_a
             if (hb[(size_t)i] < nv) continue;
             double rhs = 0.0;
             TP_CU(cudaMemcpy(&rhs, as.tab + i * as.ld + art_nv, sizeof(double), cudaMemcpyDeviceToHost));
-            if (rhs != 0.0) return finish(B200LP_ARTIFICIAL_STUCK);
+            if (ref_feas ? (rhs != 0.0) : !(std::fabs(rhs) <= thr_feas))
+                return finish(B200LP_ARTIFICIAL_NONZERO);
             std::fill(is_basic.begin(), is_basic.end(), 0);
             for (int64_t k = 0; k < m; ++k) is_basic[(size_t)hb[(size_t)k]] = 1;
             TP_CU(cudaMemcpy(d_is_basic, is_basic.data(), (size_t)C_art, cudaMemcpyHostToDevice));
-            k_first_nonzero_nonbasic<<<1, 1024, 0, as.stream>>>(as.tab + i * as.ld, (int)nv,
-                                                                d_is_basic, d_newcol);
+            if (ref_feas)
+                k_first_nonzero_nonbasic<<<1, 1024, 0, as.stream>>>(as.tab + i * as.ld, (int)nv,
+                                                                    d_is_basic, d_newcol);
+            else
+                k_largest_nonbasic<<<1, 1024, 0, as.stream>>>(as.tab + i * as.ld, (int)nv, d_is_basic,
+                                                              art->thr_pivot, d_newcol);
             int new_col = -1;
             TP_CU(cudaMemcpyAsync(&new_col, d_newcol, sizeof(int), cudaMemcpyDeviceToHost, as.stream));
             TP_CU(cudaStreamSynchronize(as.stream));
-            if (new_col < 0) return finish(B200LP_ARTIFICIAL_STUCK);
+            if (new_col < 0) {
+                if (ref_feas) return finish(B200LP_ARTIFICIAL_STUCK);
+                ++redundant;                               // a combination of the other rows: keep it
+                continue;
+            }
             if ((rc = b200lp_pivot(art, new_col, i))) return finish(rc);
             hb[(size_t)i] = new_col;
             ++cleanup;
@@ -1838,7 +1861,7 @@ int b200lp_solve_two_phase(const b200lp_opts *opts, double *art_tab, int64_t C_a
         TP_CU(cudaMemcpyAsync(ms.basis, as.basis, sizeof(int32_t) * m, cudaMemcpyDeviceToDevice, ms.stream));
         TP_CU(cudaMalloc(&d_scales, sizeof(double) * m));
         k_reprice_scales<<<(unsigned)((m + 255) / 256), 256, 0, ms.stream>>>(
-            ms.tab + m * ms.ld, ms.basis, (int)m, d_scales);
+            ms.tab + m * ms.ld, ms.basis, (int)m, (int)nv, d_scales);
         k_reprice<<<(unsigned)((nv + 1 + 127) / 128), 128, 0, ms.stream>>>(ms.tab, ms.ld, (int)m,
                                                                           (int)nv, d_scales);
         TP_CU(cudaStreamSynchronize(ms.stream));

@@ -242,7 +242,8 @@ def _opts(tableau, backend):
                           pivot_rule=backend.get("pivot_rule", _ffi.RULE_REFERENCE),
                           max_iters=backend.get("max_iterations", 0),
                           devices=backend.get("devices"),
-                          writeback_full=backend.get("writeback_full", True))
+                          writeback_full=backend.get("writeback_full", True),
+                          feas_mode=backend.get("feas_mode", _ffi.FEAS_SCALED))
 
 
 def n_solve_tableau(tableau, **backend):
@@ -286,10 +287,17 @@ def pivot_row(tableau, entering_col, changing_row):
 
 
 # ------------------------------------------------------------------------- branch and bound
+INTEGRALITY_TOLERANCE = 1e-9
+
+
 def _is_integral(value, tol_factor):
-    """The reference tests (integerp value) on exact rationals (:479); on fp64 the same question
-    is asked with its own `fp=` tolerance: |value - round(value)| <= factor * eps."""
-    return abs(value - round(value)) <= tol_factor * CL_DOUBLE_FLOAT_EPSILON
+    """The reference tests (integerp value) on exact rationals (:479).  An fp64 vertex with an
+    integer coordinate carries 1e-12..1e-10 of noise (more for values far from 1), so the question
+    is asked with a tolerance of its own, relative to the value: 1e-9 * max(1, |value|) (and never
+    tighter than the `fp=` tolerance factor * eps).  Branching on noise would add a row, a
+    phase 1 and a GPU solve per spurious node, with nothing bounding the depth."""
+    tol = max(INTEGRALITY_TOLERANCE * max(1.0, abs(value)), tol_factor * CL_DOUBLE_FLOAT_EPSILON)
+    return abs(value - round(value)) <= tol
 
 
 def violated_integer_constraint(tableau):
@@ -303,7 +311,7 @@ def violated_integer_constraint(tableau):
 def gen_entries(tableau, entry):
     """src/simplex.lisp:466-473"""
     var = violated_integer_constraint(tableau)
-    val = tableau_variable(tableau, var)
+    val = tableau_variable(tableau, var)             # fractional by more than the tolerance
     return [[("<=", [(var, 1)], math.floor(val))] + entry,
             [(">=", [(var, 1)], math.ceil(val))] + entry]
 
@@ -325,7 +333,8 @@ def b200_solver(problem, **kwargs):
     Keywords: fp_tolerance (the reference's :fp-tolerance, default 1024) plus the backend's own
     devices=[...], pivot_rule, max_iterations (allowed by solve-problem's &allow-other-keys)."""
     tol = kwargs.pop("fp_tolerance", 1024)
-    backend = {k: kwargs[k] for k in ("devices", "pivot_rule", "max_iterations") if k in kwargs}
+    backend = {k: kwargs[k] for k in ("devices", "pivot_rule", "max_iterations", "feas_mode")
+               if k in kwargs}
     better = (lambda a, b: a < b) if problem.type == "max" else (lambda a, b: a > b)
     best, solution = None, None
     stack = [[]]

@@ -12,7 +12,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle_simplex.so")
 
-OPTIMAL, UNBOUNDED, INFEASIBLE, ITERATION_LIMIT, ARTIFICIAL_STUCK = 0, 1, 2, 3, 4
+OPTIMAL, UNBOUNDED, INFEASIBLE, ITERATION_LIMIT, ARTIFICIAL_STUCK, ARTIFICIAL_NONZERO = 0, 1, 2, 3, 4, 5
+FEAS_SCALED, FEAS_REFERENCE = 0, 1
 
 _lib = None
 _c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -59,7 +60,7 @@ def lib():
             _c_double_p, ctypes.c_int64, ctypes.c_int64, _c_int32_p,
             _c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _c_int32_p,
             ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int64, ctypes.c_int,
-            _c_int64_p]
+            ctypes.c_int, _c_int64_p]
         _lib = L
     return _lib
 
@@ -123,13 +124,15 @@ def solve(tab, basis, is_max=True, tol=1024.0, rule=0, max_iters=0, parallel=Fal
 
 
 def solve_two_phase(art, art_basis, main, main_basis, is_max=True, tol=1024.0, rule=0,
-                    max_iters=0, parallel=False):
-    """In place on both tableaus. Returns (status, (phase1, cleanup, phase2) pivots)."""
+                    max_iters=0, parallel=False, feas_mode=FEAS_SCALED, with_redundant=False):
+    """In place on both tableaus. Returns (status, (phase1, cleanup, phase2) pivots)
+    [+ redundant rows when with_redundant]."""
     R, C_art, ld_art = _check_tab(art)
     R2, C, ld = _check_tab(main)
     assert R == R2
-    iters = (ctypes.c_int64 * 3)()
+    iters = (ctypes.c_int64 * 4)()
     st = lib().oracle_solve_two_phase(_dp(art), C_art, ld_art, _ip(art_basis),
                                       _dp(main), R, C, ld, _ip(main_basis),
-                                      int(is_max), tol, rule, max_iters, int(parallel), iters)
-    return st, tuple(iters)
+                                      int(is_max), tol, rule, max_iters, int(parallel),
+                                      int(feas_mode), iters)
+    return st, (tuple(iters) if with_redundant else tuple(iters)[:3])

@@ -37,8 +37,21 @@ enum {
     ORACLE_UNBOUNDED = 1,      /* src/simplex.lisp:458-459 unbounded-problem-error */
     ORACLE_INFEASIBLE = 2,     /* src/simplex.lisp:405-407 infeasible-problem-error */
     ORACLE_ITERATION_LIMIT = 3,/* build extension: the reference has no cap */
-    ORACLE_ARTIFICIAL_STUCK = 4/* src/simplex.lisp:423-424, 432-433 plain `error` */
+    ORACLE_ARTIFICIAL_STUCK = 4,/* src/simplex.lisp:432-433 plain `error`: cannot be replaced */
+    ORACLE_ARTIFICIAL_NONZERO = 5/* src/simplex.lisp:423-424 plain `error`: still non-zero */
 };
+
+/* How the two-phase transition judges "zero" (build extension):
+ * FEAS_REFERENCE: exactly the reference -- |obj| <= tol*eps absolute (:405-406), artificial
+ *   rows need RHS == 0 and a replacement column with an exactly non-zero entry (:419-434).
+ *   Right for exact-rational input, which the reference keeps exact; on fp64 it rejects
+ *   feasible problems whose phase-1 objective carries rounding residue.
+ * FEAS_SCALED (the backend's default): the same tests with the tolerance scaled by the size
+ *   of the numbers that cancelled, s = max(1, |initial phase-1 objective|): |obj| <= tol*eps*s,
+ *   artificial rows need |RHS| <= tol*eps*s, the replacement column is the non-basic column
+ *   with the LARGEST |entry| > (tol/2)*eps (first index on ties), and a row with no such column
+ *   is redundant and keeps its artificial at level zero instead of raising. */
+enum { FEAS_SCALED = 0, FEAS_REFERENCE = 1 };
 
 enum { RULE_REFERENCE = 0, RULE_BLAND = 1 };
 
@@ -176,17 +189,22 @@ int oracle_solve(double *tab, int64_t R, int64_t C, int64_t ld, int32_t *basis,
  * art: R x C_art (ld_art), its instance problem is `min` (src/simplex.lisp:317-319);
  * main: R x C (ld), min/max per is_max.  On success the main tableau holds the
  * phase-2 optimum and main_basis its basis.  iters_out[0] = phase-1 pivots,
- * iters_out[1] = artificial clean-up pivots, iters_out[2] = phase-2 pivots. */
+ * iters_out[1] = artificial clean-up pivots, iters_out[2] = phase-2 pivots,
+ * iters_out[3] = redundant rows left with a zero-level artificial (FEAS_SCALED only). */
 int oracle_solve_two_phase(double *art, int64_t C_art, int64_t ld_art, int32_t *art_basis,
                            double *mtab, int64_t R, int64_t C, int64_t ld, int32_t *main_basis,
                            int is_max, double tol, int rule, int64_t max_iters, int parallel,
-                           int64_t *iters_out)
+                           int feas_mode, int64_t *iters_out)
 {
     const int64_t m = R - 1;
     const int64_t num_vars = C - 1;         /* main var-count */
     const int64_t num_art_vars = C_art - 1; /* art var-count  */
-    int64_t it1 = 0, it_fix = 0, it2 = 0;
-    if (iters_out) iters_out[0] = iters_out[1] = iters_out[2] = 0;
+    int64_t it1 = 0, it_fix = 0, it2 = 0, redundant = 0;
+    if (iters_out) iters_out[0] = iters_out[1] = iters_out[2] = iters_out[3] = 0;
+    const double obj0 = art[m * ld_art + num_art_vars];
+    const double scale = (feas_mode == FEAS_REFERENCE) ? 1.0 : fmax(1.0, fabs(obj0));
+    const double thr_feas = tol * CL_DOUBLE_FLOAT_EPSILON * scale;
+    const double thr_pivot = (tol / 2.0) * CL_DOUBLE_FLOAT_EPSILON;
 
     int st = oracle_solve(art, R, C_art, ld_art, art_basis, /*is_max=*/0, tol, rule,
                           max_iters, parallel, &it1, NULL, NULL, 0);
@@ -195,43 +213,59 @@ int oracle_solve_two_phase(double *art, int64_t C_art, int64_t ld_art, int32_t *
 
     /* (unless (fp= 0 obj tol) (error 'infeasible-problem-error)) :405-407 */
     const double art_obj = art[m * ld_art + num_art_vars];
-    if (!(fabs(0.0 - art_obj) <= tol * CL_DOUBLE_FLOAT_EPSILON)) return ORACLE_INFEASIBLE;
+    if (!(fabs(0.0 - art_obj) <= thr_feas)) return ORACLE_INFEASIBLE;
 
     /* drive zero-level artificials out of the basis :419-434 */
     for (int64_t i = 0; i < m; ++i) {
         if (art_basis[i] >= num_vars) {
-            if (art[i * ld_art + num_art_vars] != 0.0) return ORACLE_ARTIFICIAL_STUCK;
+            const double rhs = art[i * ld_art + num_art_vars];
+            if (feas_mode == FEAS_REFERENCE ? (rhs != 0.0) : !(fabs(rhs) <= thr_feas))
+                return ORACLE_ARTIFICIAL_NONZERO;
             int64_t new_col = -1;
+            double best = 0.0;
             for (int64_t j = 0; j < num_vars; ++j) {
-                if (art[i * ld_art + j] != 0.0) {
+                const double a = art[i * ld_art + j];
+                const int cand = (feas_mode == FEAS_REFERENCE) ? (a != 0.0)
+                                                               : (fabs(a) > thr_pivot && fabs(a) > best);
+                if (cand) {
                     int in_basis = 0;
                     for (int64_t k = 0; k < m; ++k)
                         if (art_basis[k] == j) { in_basis = 1; break; }
-                    if (!in_basis) { new_col = j; break; }
+                    if (!in_basis) {
+                        new_col = j;
+                        if (feas_mode == FEAS_REFERENCE) break;
+                        best = fabs(a);
+                    }
                 }
             }
-            if (new_col < 0) return ORACLE_ARTIFICIAL_STUCK;
+            if (new_col < 0) {
+                if (feas_mode == FEAS_REFERENCE) return ORACLE_ARTIFICIAL_STUCK;
+                ++redundant;                 /* the row is a combination of the others */
+                continue;
+            }
             oracle_pivot(art, R, C_art, ld_art, art_basis, new_col, i, parallel);
             ++it_fix;
         }
     }
-    if (iters_out) iters_out[1] = it_fix;
+    if (iters_out) { iters_out[1] = it_fix; iters_out[3] = redundant; }
 
     /* copy coefficients and RHS of the constraint rows :437-441 */
     for (int64_t r = 0; r < m; ++r) {
         for (int64_t c = 0; c < num_vars; ++c) mtab[r * ld + c] = art[r * ld_art + c];
         mtab[r * ld + num_vars] = art[r * ld_art + num_art_vars];
     }
-    /* basis + re-price the objective row :444-451 */
+    /* basis + re-price the objective row :444-451 (a redundant row's artificial has no column
+     * in the main tableau: nothing to price out) */
     double *obj = mtab + m * ld;
     for (int64_t i = 0; i < m; ++i) {
         const int32_t bc = art_basis[i];
         main_basis[i] = bc;
-        const double scale = obj[bc];
-        if (scale != 0.0) {
+        if (bc >= num_vars) continue;
+        const double scale_i = obj[bc];
+        if (scale_i != 0.0) {
             const double *row = mtab + i * ld;
             for (int64_t c = 0; c <= num_vars; ++c) {
-                const double prod = scale * row[c];
+                const double prod = scale_i * row[c];
                 obj[c] = obj[c] - prod;
             }
         }

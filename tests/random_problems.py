@@ -85,6 +85,64 @@ def check(seed):
     return "optimal"
 
 
+def generate_ratio(seed):
+    """LPs whose data are RATIOS (k/3, k/7, k/10) with mostly >= and = rows: exact in the
+    reference, rounded on entry to an fp64 backend -- the phase-1 objective then ends at a residue
+    of a few 1e-13 instead of 0, which an absolute 1024*eps test calls infeasible."""
+    from fractions import Fraction
+    rng = np.random.default_rng(50_000 + seed)
+    n = int(rng.integers(2, 7))
+    m = int(rng.integers(2, 6))
+    names = [f"r{i}" for i in range(n)]
+    dens = (1, 3, 7, 10)
+
+    def frac(lo, hi):
+        return Fraction(int(rng.integers(lo, hi)), int(dens[int(rng.integers(0, 4))]))
+
+    c = [frac(1, 20) for _ in range(n)]                    # min with positive costs: bounded below
+    forms, A_ub, b_ub, A_eq, b_eq = [], [], [], [], []
+    x0 = [frac(0, 30) for _ in range(n)]                   # most rows are built around a feasible point
+    for _ in range(m):
+        a = [frac(0, 12) if rng.random() < 0.8 else Fraction(0) for _ in range(n)]
+        if sum(1 for v in a if v) < 2:
+            a[0], a[1] = frac(1, 12), frac(1, 12)
+        at_x0 = sum(ai * xi for ai, xi in zip(a, x0))
+        op = (">=", "=", "<=")[int(rng.choice(3, p=[0.5, 0.3, 0.2]))]
+        rhs = at_x0 if op == "=" else at_x0 - frac(0, 9) if op == ">=" else at_x0 + frac(0, 9)
+        if rng.random() < 0.1:
+            rhs = rhs + frac(5, 40)                         # sometimes off the feasible point
+        rhs = max(rhs, Fraction(0))
+        lhs = "(+ " + " ".join(f"(* {k} {v})" for k, v in zip(a, names) if k) + ")"
+        forms.append(f"({op} {lhs} {rhs})")
+        af = [float(v) for v in a]
+        if op == "<=":
+            A_ub.append(af); b_ub.append(float(rhs))
+        elif op == ">=":
+            A_ub.append([-v for v in af]); b_ub.append(-float(rhs))
+        else:
+            A_eq.append(af); b_eq.append(float(rhs))
+    objective = "(min (+ " + " ".join(f"(* {k} {v})" for k, v in zip(c, names)) + "))"
+    kw = dict(A_ub=np.array(A_ub) if A_ub else None, b_ub=b_ub or None,
+              A_eq=np.array(A_eq) if A_eq else None, b_eq=b_eq or None,
+              bounds=[(0, None)] * n, method="highs")
+    ref = linprog([float(v) for v in c], **kw)
+    return objective, forms, names, ref
+
+
+def check_ratio(seed):
+    objective, forms, names, ref = generate_ratio(seed)
+    problem = P.make_linear_problem(objective, *forms)
+    try:
+        sol = solver.solve_problem(problem)
+    except conditions.InfeasibleProblemError:
+        assert ref.status == 2, (seed, "backend: infeasible", ref.status, ref.message)
+        return "infeasible"
+    assert ref.status == 0, (seed, "backend: optimal", ref.status, ref.message)
+    got = solver.solution_objective_value(sol)
+    assert abs(got - ref.fun) <= 1e-7 * max(1.0, abs(ref.fun)), (seed, got, ref.fun)
+    return "optimal"
+
+
 def check_integer(seed):
     """A random small pure-integer LP through the hook's branch and bound, against scipy's MILP."""
     from scipy.optimize import Bounds, LinearConstraint, milp

@@ -271,6 +271,31 @@ def test_degenerate_lp_basis_bit_exact(rule):
 
 
 # ------------------------------------------------------------------ two-phase, randomized
+@pytest.mark.parametrize("feas_mode", [0, 1], ids=["scaled", "reference"])
+@pytest.mark.parametrize("seed", range(40))
+def test_two_phase_ratio_problems_match_oracle_in_both_feasibility_modes(seed, feas_mode):
+    """The transition's "is it zero" tests (src/simplex.lisp:405-434) in both modes
+    (include/b200lp.h B200LP_FEAS_*): status, pivot counts, redundant rows and both tableaus equal
+    the oracle's, bit for bit -- including the LPs the literal mode rejects."""
+    import random_problems
+    from linear_programming_b200 import problem as P, simplex
+    objective, forms, names, ref = random_problems.generate_ratio(seed)
+    problem = P.make_linear_problem(objective, *forms)
+    built = simplex.build_tableau(problem, problem)
+    if not isinstance(built, list):
+        pytest.skip("no artificial rows")
+    art, main = built
+    o = [x.copy() for x in (art.matrix, art.basis_columns, main.matrix, main.basis_columns)]
+    ost, oits = oracle.solve_two_phase(*o, False, feas_mode=feas_mode, with_redundant=True)
+    st, res = _ffi.solve_two_phase(art.matrix, art.basis_columns, main.matrix, main.basis_columns,
+                                   False, _ffi.make_opts(writeback_full=True, feas_mode=feas_mode))
+    assert st == ost
+    if st in (_ffi.OK, _ffi.UNBOUNDED):
+        assert (res.iterations_phase1, res.iterations_cleanup, res.iterations, res.redundant_rows) == oits
+        assert np.array_equal(main.matrix, o[2]) and np.array_equal(main.basis_columns, o[3])
+        assert np.array_equal(art.matrix, o[0]) and np.array_equal(art.basis_columns, o[1])
+
+
 @pytest.mark.parametrize("seed", [1, 2, 3])
 def test_two_phase_random_matches_oracle(seed):
     """>= and = rows need artificials (src/simplex.lisp:258-263, 288-325)."""

@@ -47,3 +47,25 @@ def test_random_integer_problems_on_the_gpu():
     import random_problems
     for seed in range(40):
         random_problems.check_integer(seed)
+
+
+def test_ratio_coefficient_two_phase_problems_agree_with_highs_on_the_gpu():
+    """600 LPs with k/3, k/7, k/10 data and >= / = rows through the real backend: with the scaled
+    feasibility / clean-up tests (the default) verdict and objective match HiGHS on every one."""
+    import collections
+    import random_problems
+    verdicts = collections.Counter(random_problems.check_ratio(seed) for seed in range(600))
+    assert verdicts["optimal"] > 300 and verdicts["infeasible"] > 10, verdicts
+
+
+def test_redundant_equality_row_is_kept_not_an_error():
+    """A duplicated `=` row leaves an artificial basic at level zero with nothing to replace it.
+    The reference raises a plain `error` there (src/simplex.lisp:432-433, reproduced by
+    feas_mode=FEAS_REFERENCE); the default treats the row as redundant and solves the LP."""
+    from linear_programming_b200 import _ffi, conditions
+    forms = ["(= (+ x y) 4)", "(= (+ x y) 4)", "(<= (+ x (* 2 y)) 6)"]
+    p = P.make_linear_problem("(max (+ x y))", *forms)
+    sol = solver.solve_problem(p)
+    assert solver.solution_objective_value(sol) == 4.0
+    with pytest.raises(conditions.SolverError, match="cannot be replaced"):
+        solver.solve_problem(p, feas_mode=_ffi.FEAS_REFERENCE)

@@ -23,7 +23,8 @@ def oracle_n_solve_tableau(tableau, **backend):
         art, main = tableau
         st, _ = oracle.solve_two_phase(art.matrix, art.basis_columns, main.matrix,
                                        main.basis_columns, main.instance_problem.type == "max",
-                                       tol=float(main.fp_tolerance_factor))
+                                       tol=float(main.fp_tolerance_factor),
+                                       feas_mode=backend.get("feas_mode", oracle.FEAS_SCALED))
         conditions.raise_for_status(st)
         return main
     st, _, _ = oracle.solve(tableau.matrix, tableau.basis_columns,
@@ -201,7 +202,8 @@ def test_status_codes_map_onto_the_reference_conditions():
     """include/b200lp.h status codes -> src/conditions.lisp:43-77"""
     conditions.raise_for_status(0)
     for code, exc in [(1, conditions.UnboundedProblemError), (2, conditions.InfeasibleProblemError),
-                      (3, conditions.SolverError), (4, conditions.SolverError)]:
+                      (3, conditions.SolverError), (4, conditions.SolverError),
+                      (5, conditions.SolverError)]:
         with pytest.raises(exc):
             conditions.raise_for_status(code)
     assert issubclass(conditions.InfeasibleIntegerConstraintsError, conditions.InfeasibleProblemError)
@@ -223,6 +225,36 @@ def test_random_integer_problems_agree_with_a_milp_solver(oracle_device):
     import random_problems
     for seed in range(80):
         random_problems.check_integer(seed)
+
+
+def test_ratio_coefficient_two_phase_problems_agree_with_highs(oracle_device):
+    """LPs with k/3, k/7, k/10 data and >= / = rows (phase 1 on every one): the reference solves
+    them exactly; an fp64 backend ends phase 1 at a residue of a few 1e-13, which the reference's
+    ABSOLUTE 1024*eps feasibility test and exact `/= 0` clean-up tests then misjudge.  With the
+    backend's scaled tests (B200LP_FEAS_SCALED, the default) every verdict and objective agrees
+    with HiGHS; with the literal ones (B200LP_FEAS_REFERENCE) some feasible LPs are rejected --
+    kept visible here so the deviation stays a documented choice."""
+    import collections
+    import random_problems
+    verdicts = collections.Counter(random_problems.check_ratio(seed) for seed in range(600))
+    assert verdicts["optimal"] > 300 and verdicts["infeasible"] > 10, verdicts
+    wrong = 0
+    for seed in range(600):
+        objective, forms, names, ref = random_problems.generate_ratio(seed)
+        if ref.status != 0:
+            continue
+        try:
+            solver.solve_problem(P.make_linear_problem(objective, *forms), feas_mode=oracle.FEAS_REFERENCE)
+        except conditions.SolverError:
+            wrong += 1
+    assert wrong >= 1, "the literal absolute tests no longer misjudge any fp64 residue?"
+
+
+def test_integrality_test_tolerates_fp64_noise_but_not_fractions():
+    """simplex._is_integral: 1e-9 * max(1, |v|), never tighter than factor * eps."""
+    assert simplex._is_integral(3.0000000000004, 1024) and simplex._is_integral(1e6 + 2e-5, 1024)
+    assert not simplex._is_integral(3.00001, 1024) and not simplex._is_integral(0.5, 1024)
+    assert simplex._is_integral(7.0, 1024) and simplex._is_integral(-2.0 - 1e-12, 1024)
 
 
 def test_dense_block_equals_the_rows_of_the_full_generator():

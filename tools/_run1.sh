@@ -1,3 +1,4 @@
 export B200LP_SPIN_TIMEOUT_MS=8000
-timeout 900 python bench.py > gpurun_out/r02_j_bench_n1.json 2> gpurun_out/r02_j_bench_n1.err
-tail -3 gpurun_out/r02_j_bench_n1.err; cat gpurun_out/r02_j_bench_n1.json
+timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -8 > gpurun_out/r02_k_pytest.log
+tail -8 gpurun_out/r02_k_pytest.log
+python __graft_entry__.py smoke 2>&1 | tail -2
