@@ -28,6 +28,7 @@
 #include "../../include/b200lp.h"
 #include "kernels.cuh"
 #include "persist.cuh"
+#include "small.cuh"
 #include "nccl_dyn.h"
 
 namespace b200lp {
@@ -1417,6 +1418,177 @@ static void release(b200lp_solver *s)
     b200lp_destroy(s);
 }
 
+// ---- single-CTA path for tableaus that fit in shared memory (small.cuh) ----------------------------
+// One context per device: a stream and a mapped pinned buffer the kernel reads its input from and
+// writes its results to (zero-copy: one launch + one synchronise per solve, no cudaMemcpy calls).
+struct SmallCtx {
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    unsigned char *h_buf = nullptr;
+    size_t cap = 0;
+    bool attr_set = false;
+};
+static SmallCtx g_small[kMaxDeviceLocks];
+static constexpr size_t kSmallSmemMax = 225 * 1024;
+
+static bool small_enabled()
+{
+    const char *e = getenv("B200LP_SMALL");          // B200LP_SMALL=0: always take the big path
+    return !(e && e[0] == '0');
+}
+
+static bool small_ok(const b200lp_opts *o, int64_t R, int64_t C_in, int64_t C_main)
+{
+    if (!small_enabled()) return false;
+    if (o && (o->ndev > 1 || o->pivot_variant != 0 || o->poll_interval != 0 || o->time_kernels != 0))
+        return false;
+    if (R < 2 || C_main < 2 || C_in < C_main || R > 8192 || C_in > 28000) return false;
+    return small_smem_bytes((int)R, (int)C_in, (int)C_main) <= kSmallSmemMax;
+}
+
+static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// b200lp_solve (art_tab == nullptr) or b200lp_solve_two_phase on one CTA.
+static int solve_small(const b200lp_opts *opts, double *art_tab, int64_t C_art, int64_t ld_art,
+                       int32_t *art_basis, double *tab, int64_t R, int64_t C, int64_t ld,
+                       int32_t *basis, int32_t is_max, b200lp_result *out, int32_t *trace_j,
+                       int32_t *trace_r)
+{
+    const double t0 = now_ms();
+    const bool two = art_tab != nullptr;
+    int ndev = 0;
+    cudaError_t e0 = cudaGetDeviceCount(&ndev);
+    if (e0 != cudaSuccess || ndev <= 0) {
+        (void)cudaGetLastError();
+        return fail(B200LP_ERR_NO_DEVICE, "cudaGetDeviceCount",
+                    e0 != cudaSuccess ? cudaGetErrorString(e0) : "no CUDA device");
+    }
+    const int device = opts ? opts->devices[0] : 0;
+    SmallCtx &cx = g_small[((device % kMaxDeviceLocks) + kMaxDeviceLocks) % kMaxDeviceLocks];
+    std::lock_guard<std::mutex> lk(cx.mu);
+    CU_TRY(cudaSetDevice(device));
+    const bool wb = opts && opts->writeback_full;
+    const int tcap = (!two && opts && opts->trace_capacity > 0) ? opts->trace_capacity : 0;
+    const int64_t C_in = two ? C_art : C;
+    // buffer layout
+    size_t off = 0;
+    const size_t o_in = off;      off = align16(off + sizeof(double) * R * C_in);
+    const size_t o_inb = off;     off = align16(off + sizeof(int32_t) * (R - 1));
+    const size_t o_mobj = off;    off = align16(off + sizeof(double) * C);
+    const size_t o_hdr = off;     off = align16(off + sizeof(SmallHeader));
+    const size_t o_rhs = off;     off = align16(off + sizeof(double) * R);
+    const size_t o_obj = off;     off = align16(off + sizeof(double) * C);
+    const size_t o_basis = off;   off = align16(off + sizeof(int32_t) * (R - 1));
+    const size_t o_full = off;    off = align16(off + (wb ? sizeof(double) * R * C : 0));
+    const size_t o_afull = off;   off = align16(off + (wb && two ? sizeof(double) * R * C_in : 0));
+    const size_t o_abasis = off;  off = align16(off + (wb && two ? sizeof(int32_t) * (R - 1) : 0));
+    const size_t o_trace = off;   off = align16(off + sizeof(int2) * (size_t)tcap);
+    if (off > cx.cap) {
+        if (cx.h_buf) cudaFreeHost(cx.h_buf);
+        cx.h_buf = nullptr; cx.cap = 0;
+        const size_t want = std::max<size_t>(off, 1u << 20);
+        CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&cx.h_buf), want, cudaHostAllocMapped));
+        cx.cap = want;
+    }
+    if (!cx.stream) CU_TRY(cudaStreamCreateWithFlags(&cx.stream, cudaStreamNonBlocking));
+    if (!cx.attr_set) {
+        CU_TRY(cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)kSmallSmemMax));
+        cx.attr_set = true;
+    }
+    unsigned char *hb = cx.h_buf;
+    unsigned char *db = nullptr;
+    CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&db), hb, 0));
+    // stage the input (packed rows)
+    {
+        const double *src = two ? art_tab : tab;
+        const int64_t lds = two ? ld_art : ld;
+        double *dst = reinterpret_cast<double *>(hb + o_in);
+        for (int64_t r = 0; r < R; ++r) std::memcpy(dst + r * C_in, src + r * lds, sizeof(double) * C_in);
+        std::memcpy(hb + o_inb, two ? art_basis : basis, sizeof(int32_t) * (R - 1));
+        if (two) std::memcpy(hb + o_mobj, tab + (R - 1) * ld, sizeof(double) * C);
+        reinterpret_cast<SmallHeader *>(hb + o_hdr)->status = ST_RUNNING;
+    }
+    double tol = (opts && opts->fp_tolerance_factor > 0) ? opts->fp_tolerance_factor : 1024.0;
+    SmallArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.in_tab = reinterpret_cast<const double *>(db + o_in);
+    a.in_basis = reinterpret_cast<const int32_t *>(db + o_inb);
+    a.main_obj = reinterpret_cast<const double *>(db + o_mobj);
+    a.R = (int)R; a.C_in = (int)C_in; a.C_main = (int)C;
+    a.two_phase = two ? 1 : 0; a.is_max = is_max ? 1 : 0; a.rule = opts ? opts->pivot_rule : 0;
+    a.feas_reference = (opts && opts->feas_mode == B200LP_FEAS_REFERENCE) ? 1 : 0;
+    b200lp_thresholds(tol, &a.thr_enter, &a.thr_pivot, &a.thr_feas);
+    a.max_iters = opts ? opts->max_iters : 0;
+    a.hdr = reinterpret_cast<SmallHeader *>(db + o_hdr);
+    a.out_rhs = reinterpret_cast<double *>(db + o_rhs);
+    a.out_obj = reinterpret_cast<double *>(db + o_obj);
+    a.out_basis = reinterpret_cast<int32_t *>(db + o_basis);
+    a.out_full = wb ? reinterpret_cast<double *>(db + o_full) : nullptr;
+    a.out_art_full = (wb && two) ? reinterpret_cast<double *>(db + o_afull) : nullptr;
+    a.out_art_basis = (wb && two) ? reinterpret_cast<int32_t *>(db + o_abasis) : nullptr;
+    a.trace = tcap ? reinterpret_cast<int2 *>(db + o_trace) : nullptr;
+    a.trace_cap = tcap;
+    const size_t smem = small_smem_bytes((int)R, (int)C_in, (int)C);
+    const double t1 = now_ms();
+    k_small<<<1, kSmallThreads, smem, cx.stream>>>(a);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(cx.stream));
+    const double t2 = now_ms();
+    const SmallHeader h = *reinterpret_cast<const SmallHeader *>(hb + o_hdr);
+    if (h.status == ST_RUNNING) return fail(B200LP_ERR_INTERNAL, "solve", "k_small left no verdict");
+    const int status = h.status;
+    int tl = 0;
+    const bool have = h.wrote != 0;    // the solve reached (and solved) the tableau the caller reads back
+    if (have) {
+        const double *rhs = reinterpret_cast<const double *>(hb + o_rhs);
+        const double *obj = reinterpret_cast<const double *>(hb + o_obj);
+        if (wb) {
+            const double *full = reinterpret_cast<const double *>(hb + o_full);
+            for (int64_t r = 0; r < R; ++r) std::memcpy(tab + r * ld, full + r * C, sizeof(double) * C);
+            if (two) {
+                const double *af = reinterpret_cast<const double *>(hb + o_afull);
+                for (int64_t r = 0; r < R; ++r)
+                    std::memcpy(art_tab + r * ld_art, af + r * C_in, sizeof(double) * C_in);
+                std::memcpy(art_basis, hb + o_abasis, sizeof(int32_t) * (R - 1));
+            }
+        } else {
+            for (int64_t i = 0; i < R; ++i) tab[i * ld + (C - 1)] = rhs[i];
+            std::memcpy(tab + (R - 1) * ld, obj, sizeof(double) * C);
+        }
+        std::memcpy(basis, hb + o_basis, sizeof(int32_t) * (R - 1));
+        if (tcap) {
+            tl = (int)std::min<long long>(h.iters, tcap);
+            const int2 *tr = reinterpret_cast<const int2 *>(hb + o_trace);
+            for (int q = 0; q < tl; ++q) {
+                if (trace_j) trace_j[q] = tr[q].x;
+                if (trace_r) trace_r[q] = tr[q].y;
+            }
+        }
+    }
+    if (out) {
+        std::memset(out, 0, sizeof(*out));
+        out->status = status;
+        out->n_devices = 1;
+        out->iterations = h.iters;
+        out->iterations_phase1 = h.iters_phase1;
+        out->iterations_cleanup = h.iters_cleanup;
+        out->redundant_rows = h.redundant;
+        out->objective = h.objective;
+        out->ms_h2d = t1 - t0;
+        out->ms_solve = t2 - t1;
+        out->kernel_launches = 1;
+        out->loop_mode = 3;
+        out->h2d_bytes = (int64_t)(sizeof(double) * R * C_in + sizeof(int32_t) * (R - 1) + (two ? sizeof(double) * C : 0));
+        out->d2h_bytes = (int64_t)(sizeof(SmallHeader) + sizeof(double) * (R + C) + sizeof(int32_t) * (R - 1) +
+                                   (wb ? sizeof(double) * R * C : 0) + sizeof(int2) * (size_t)tl);
+        out->bytes_per_pivot = 16 * R * C;
+        out->trace_len = tl;
+        out->ms_total = now_ms() - t0;
+    }
+    return status;
+}
+
 } // namespace b200lp
 
 // =============================================================================================
@@ -1452,6 +1624,16 @@ void b200lp_abi_sizes(int64_t *opts_size, int64_t *result_size)
 
 void b200lp_shutdown(void)
 {
+    for (int d = 0; d < kMaxDeviceLocks; ++d) {
+        SmallCtx &cx = g_small[d];
+        std::lock_guard<std::mutex> lk(cx.mu);
+        if (cx.h_buf || cx.stream) {
+            cudaSetDevice(d);
+            if (cx.stream) { cudaStreamSynchronize(cx.stream); cudaStreamDestroy(cx.stream); }
+            if (cx.h_buf) cudaFreeHost(cx.h_buf);
+            cx.stream = nullptr; cx.h_buf = nullptr; cx.cap = 0;
+        }
+    }
     std::vector<b200lp_solver *> idle;
     {
         std::lock_guard<std::mutex> lk(g_pool_mu);
@@ -1700,6 +1882,13 @@ int b200lp_solve(const b200lp_opts *opts, double *tab, int64_t R, int64_t C, int
                  int32_t *trace_r)
 {
     if (!tab || !basis || ld < C) return fail(B200LP_ERR_INVALID_ARG, "solve", "null buffer or ld < C");
+    if (small_ok(opts, R, C, C)) {
+        try {
+            return solve_small(opts, nullptr, 0, 0, nullptr, tab, R, C, ld, basis, is_max, out, trace_j, trace_r);
+        } catch (const std::exception &ex) {
+            return fail(B200LP_ERR_INTERNAL, "solve", ex.what());
+        }
+    }
     const double t0 = now_ms();
     b200lp_solver *s = nullptr;
     RC_TRY(acquire(opts, R, C, is_max, &s));
@@ -1750,6 +1939,14 @@ int b200lp_solve_two_phase(const b200lp_opts *opts, double *art_tab, int64_t C_a
 {
     if (!art_tab || !art_basis || !main_tab || !main_basis || ld_art < C_art || ld < C || C_art < C)
         return fail(B200LP_ERR_INVALID_ARG, "solve_two_phase", "null buffer or bad dimensions");
+    if (small_ok(opts, R, C_art, C)) {
+        try {
+            return solve_small(opts, art_tab, C_art, ld_art, art_basis, main_tab, R, C, ld, main_basis,
+                               is_max, out, nullptr, nullptr);
+        } catch (const std::exception &ex) {
+            return fail(B200LP_ERR_INTERNAL, "solve_two_phase", ex.what());
+        }
+    }
     // The phase transition re-prices the objective row over ALL rows in order (:444-451), so the
     // two-phase variant runs on one GPU: with several devices requested it uses devices[0].
     b200lp_opts one;

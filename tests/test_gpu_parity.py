@@ -15,6 +15,15 @@ from oracle import oracle
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["1", "0"], ids=["one-cta-on", "one-cta-off"])
+def small_path(request, monkeypatch):
+    """Tableaus that fit one CTA's shared memory are solved by k_small (one launch per solve);
+    B200LP_SMALL=0 sends them down the big path (k_persist / k_iter) instead.  Both must equal the
+    oracle bit for bit."""
+    monkeypatch.setenv("B200LP_SMALL", request.param)
+    return request.param == "1"
+
+
 def f64(rows):
     return np.array([[float(x) for x in r] for r in rows], dtype=np.float64)
 
@@ -44,7 +53,7 @@ def test_pivot_row_golden():
     assert out[-1, -1] == 4.0
 
 
-def test_basic_problem_golden():
+def test_basic_problem_golden(small_path):
     """t/simplex.lisp:170-194, README.md:58-62"""
     g = G.BASIC_SOLVED
     tab, basis = f64(g["initial"]["matrix"]), i32(g["initial"]["basis"])
@@ -52,6 +61,7 @@ def test_basic_problem_golden():
     assert st == _ffi.OK and res.iterations == g["pivots"] and trace == g["trace"]
     assert np.array_equal(tab, f64(g["matrix"])) and basis.tolist() == g["basis"]
     assert res.objective == 28.5
+    assert res.loop_mode == (3 if small_path else 2) and (res.kernel_launches == 1 or not small_path)
 
 
 def test_basic_problem_partial_writeback_touches_only_solution_cells():
@@ -67,7 +77,7 @@ def test_basic_problem_partial_writeback_touches_only_solution_cells():
 
 
 @pytest.mark.parametrize("g", [G.EQ_SOLVED, G.GEQ_SOLVED], ids=["eq", "geq"])
-def test_two_phase_goldens(g):
+def test_two_phase_goldens(g, small_path):
     """t/simplex.lisp:196-275"""
     b = g["initial"]
     art, ab = f64(b["art_matrix"]), i32(b["art_basis"])
@@ -83,7 +93,7 @@ def test_two_phase_goldens(g):
     assert abs(res.objective - float(g["objective"])) <= 1e-8 * float(g["objective"])
 
 
-def test_unsolvable_problems():
+def test_unsolvable_problems(small_path):
     """t/simplex.lisp:277-289"""
     g = G.INFEASIBLE
     st, _ = _ffi.solve_two_phase(f64(g["art_matrix"]), i32(g["art_basis"]),
@@ -94,7 +104,7 @@ def test_unsolvable_problems():
     assert st == _ffi.UNBOUNDED
 
 
-def test_assembly_problem():
+def test_assembly_problem(small_path):
     """t/integration.lisp:32-58"""
     g = G.ASSEMBLY
     tab, basis = f64(g["matrix"]), i32(g["basis"])
@@ -134,7 +144,7 @@ def test_each_reference_function_matches_oracle(m, n, signed):
 
 @pytest.mark.parametrize("m,n,is_max", [(64, 96, True), (256, 512, True), (100, 40, True),
                                         (96, 160, False), (1, 3, True), (3, 1, True)])
-def test_full_solve_bit_exact(m, n, is_max):
+def test_full_solve_bit_exact(m, n, is_max, small_path):
     tab, basis = random_tableau(m, n, seed=11 * m + n)
     if not is_max:
         tab[-1, :n] *= -1.0          # min (-c).x: the objective row (still -coef, :272) is +c
@@ -161,7 +171,7 @@ def test_config2_m1024_n2048_objective_and_basis():
     assert abs(res.objective - 545.8113461511593) <= 1e-8 * 545.8113461511593   # HiGHS, SURVEY 6
 
 
-def test_padded_host_leading_dimension():
+def test_padded_host_leading_dimension(small_path):
     tab0, basis = random_tableau(50, 70, seed=5)
     wide = np.full((tab0.shape[0], tab0.shape[1] + 13), np.nan)
     wide[:, :tab0.shape[1]] = tab0
@@ -193,7 +203,7 @@ def test_iteration_limit_and_resume():
     assert st == _ffi.ITERATION_LIMIT and res.iterations == 3
 
 
-def test_fp_tolerance_keyword_changes_thresholds_like_the_oracle():
+def test_fp_tolerance_keyword_changes_thresholds_like_the_oracle(small_path):
     tab, basis = random_tableau(60, 90, seed=21)
     for tol in (1.0, 1024.0, 1e9):
         o_tab, o_basis = tab.copy(), basis.copy()
@@ -239,7 +249,7 @@ def test_persistent_loop_any_look_grid_is_bit_exact(m, n, rule, look_ctas, monke
 
 
 # ------------------------------------------------------------------ degenerate / Bland (config 5)
-def test_beale_cycles_under_reference_rule_and_bland_terminates():
+def test_beale_cycles_under_reference_rule_and_bland_terminates(small_path):
     g = G.BEALE
     tab, basis = f64(g["matrix"]), i32(g["basis"])
     o_tab, o_basis = tab.copy(), basis.copy()
@@ -273,7 +283,7 @@ def test_degenerate_lp_basis_bit_exact(rule):
 # ------------------------------------------------------------------ two-phase, randomized
 @pytest.mark.parametrize("feas_mode", [0, 1], ids=["scaled", "reference"])
 @pytest.mark.parametrize("seed", range(40))
-def test_two_phase_ratio_problems_match_oracle_in_both_feasibility_modes(seed, feas_mode):
+def test_two_phase_ratio_problems_match_oracle_in_both_feasibility_modes(seed, feas_mode, small_path):
     """The transition's "is it zero" tests (src/simplex.lisp:405-434) in both modes
     (include/b200lp.h B200LP_FEAS_*): status, pivot counts, redundant rows and both tableaus equal
     the oracle's, bit for bit -- including the LPs the literal mode rejects."""
@@ -297,7 +307,7 @@ def test_two_phase_ratio_problems_match_oracle_in_both_feasibility_modes(seed, f
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3])
-def test_two_phase_random_matches_oracle(seed):
+def test_two_phase_random_matches_oracle(seed, small_path):
     """>= and = rows need artificials (src/simplex.lisp:258-263, 288-325)."""
     rng = np.random.default_rng(seed)
     m, n = 40, 30
@@ -460,11 +470,13 @@ def _sweep_cases():
     return cases
 
 
+@pytest.mark.parametrize("small", ["1", "0"], ids=["one-cta-path-on", "one-cta-path-off"])
 @pytest.mark.parametrize("m,n,seed", _sweep_cases())
-def test_random_shapes_signs_rules_bit_exact(m, n, seed):
+def test_random_shapes_signs_rules_bit_exact(m, n, seed, small, monkeypatch):
     """Mixed-sign data (optimal, unbounded and stalled outcomes all occur), max and min problems,
     both pivot rules, every row-stride alignment; status, pivot trace, basis and every cell must
     equal the oracle's."""
+    monkeypatch.setenv("B200LP_SMALL", small)       # "0": tableaus that fit one CTA take the big path too
     rng = np.random.default_rng(seed)
     A = rng.random((m, n)) - (0.0 if seed % 3 else 0.3)
     if seed % 4 == 0:
@@ -488,7 +500,7 @@ def test_random_shapes_signs_rules_bit_exact(m, n, seed):
     assert np.array_equal(basis, o_basis) and np.array_equal(tab, o_tab)
 
 
-def test_pooled_handles_are_rebound_cleanly_across_shapes():
+def test_pooled_handles_are_rebound_cleanly_across_shapes(small_path):
     """The one-shot calls reuse idle handles for nearby shapes; nothing of a previous solve (ring
     slots, ping-pong parity, basis, trace, tolerances, rule) may leak into the next."""
     shapes = [(30, 40), (31, 41), (12, 90), (33, 38), (2, 3), (60, 100), (30, 40), (64, 190), (5, 7)]
