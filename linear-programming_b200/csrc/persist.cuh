@@ -46,6 +46,15 @@ constexpr int ST_SPIN_TIMEOUT = -6;      // == B200LP_ERR_INTERNAL
 constexpr int kPLookMax = 16;            // look CTAs of k_persist
 constexpr int kPUnits = 4;               // double2 column units a look thread loads per batch
 
+// Loop state of the look role.  k_persist keeps it in registers for the whole call; k_iter2 runs
+// one decision per launch and parks it here in between.
+struct alignas(16) LookCarry {
+    long long fin_at;          // decision index at which the solve ended (0 = still running)
+    long long iters;           // pivots completed
+    unsigned long long bar_n[2];
+    int j, j_prev, p_prev, w_prev;
+};
+
 // Every hot word has its own 128-byte line: `decided` is polled by every tile CTA, done[] takes
 // their atomics, bar[] the look CTAs' -- sharing a line makes each of them wait for the others.
 struct alignas(128) PSync {
@@ -61,6 +70,8 @@ struct alignas(128) PSync {
     unsigned long long gt0, clk0, gt1, clk1;
     unsigned long long dbg[8];                    // finer stamps of the lead thread (cycles, summed)
     alignas(128) Cand part[2][kPLookMax];
+    // k_iter2 (one launch per pivot): what the look role carries from one launch to the next
+    alignas(128) LookCarry carry;
 };
 
 // Exchange layout of the persistent loop (inside the same peer-mapped buffer k_iter uses):
@@ -197,7 +208,12 @@ __device__ __forceinline__ void enter_scan(Cand &best, const double o, const int
 }
 
 // ---- look role ---------------------------------------------------------------------------------
-__device__ __forceinline__ void persist_look(const PersistArgs &P, const int cta, const int G)
+// ONE_STEP = false: the whole loop (k_persist).  ONE_STEP = true: decision `k_one` only (k_iter2:
+// launch L decides pivot L + 1; the previous launch is complete, so there is nothing to wait for);
+// the loop state comes from / goes back to PSync::carry.
+template <bool ONE_STEP>
+__device__ __forceinline__ void persist_look(const PersistArgs &P, const int cta, const int G,
+                                             const long long k_one)
 {
     __shared__ Cand red[kLookThreads / 32];
     __shared__ Cand s_part;
@@ -213,14 +229,24 @@ __device__ __forceinline__ void persist_look(const PersistArgs &P, const int cta
     const int v_begin = cta * chunkV, v_end = min(ldv, v_begin + chunkV);
     const int chunkR = (P.R_local + G - 1) / G;
     const int r_begin = cta * chunkR, r_end = min(P.R_local, r_begin + chunkR);
+    long long iters = P.iters0;
+    int j = -1;
+    int j_prev = -1, p_prev = -1, w_prev = 0;
+    Cand best;
+    best.q = 0.0; best.key = 0; best.row = -1;
+    if (ONE_STEP && k_one > 1) {
+        const LookCarry *c = &S->carry;
+        iters = __ldcg(&c->iters);
+        bar_n[0] = __ldcg(&c->bar_n[0]); bar_n[1] = __ldcg(&c->bar_n[1]);
+        j = __ldcg(&c->j); j_prev = __ldcg(&c->j_prev);
+        p_prev = __ldcg(&c->p_prev); w_prev = __ldcg(&c->w_prev);
+    } else {
     if (lead) {
         S->gt0 = global_timer_ns();
         S->clk0 = (unsigned long long)clock64();
     }
 
     // ---- prologue: compact copies of S_0's objective row / RHS column; entering column of pivot 1
-    Cand best;
-    best.q = 0.0; best.key = 0; best.row = -1;
     {
         const double *S0 = P.tab[0];
         const double *obj = S0 + (int64_t)P.m_local * P.ld;
@@ -240,8 +266,6 @@ __device__ __forceinline__ void persist_look(const PersistArgs &P, const int cta
         if (!look_bar(S, 1, bar_n[1], P.timeout_ns)) return;
         best = preduce(S->part[1], G, &s_part);
     }
-    long long iters = P.iters0;
-    int j = -1;
     {
         const bool accept = (best.row >= 0) && (P.rule != 0 || best.q < 0.0 - P.thr_enter);
         int fin = ST_RUNNING;
@@ -255,21 +279,22 @@ __device__ __forceinline__ void persist_look(const PersistArgs &P, const int cta
                 P.ring[(1 + P.slot_base) & (kRing - 1)] = o;
                 P.report->iters = iters;
                 P.report->status = fin;
+                S->carry.fin_at = 1;
                 __threadfence();
                 *reinterpret_cast<volatile unsigned long long *>(&S->decided) = 1ull;
             }
             return;
         }
     }
+    }   // prologue
 
-    int j_prev = -1, p_prev = -1, w_prev = 0;
-    for (long long k = 1;; ++k) {
+    for (long long k = ONE_STEP ? k_one : 1;; ++k) {
         const int slot = (int)((k + P.slot_base) & (kRing - 1));
         const int pslot = (int)((k - 1 + P.slot_base) & (kRing - 1));
         const bool pending = k >= 2;
         const double *src = P.tab[pending ? (int)(k & 1) : 0];       // S_{k-2} (S_0 for k = 1)
         const long long t0 = lead ? clock64() : 0ll;
-        if (k >= 3) {
+        if (!ONE_STEP && k >= 3) {
             // S_{k-2} must be complete: every tile CTA has finished update(k-2)
             const unsigned long long want = T * (unsigned long long)((k - 3) / kRing + 1);
             if (!cta_wait_ge(&S->done[(k - 2) & (kRing - 1)], want, S, P.timeout_ns, ST_SPIN_TIMEOUT))
@@ -482,6 +507,7 @@ __device__ __forceinline__ void persist_look(const PersistArgs &P, const int cta
                 P.ring[slot] = o;
                 P.report->iters = iters;
                 P.report->status = ST_UNBOUNDED;
+                S->carry.fin_at = k;
                 __threadfence();
                 *reinterpret_cast<volatile unsigned long long *>(&S->decided) = (unsigned long long)k;
             }
@@ -517,6 +543,13 @@ __device__ __forceinline__ void persist_look(const PersistArgs &P, const int cta
                 P.ring[(k + 1 + P.slot_base) & (kRing - 1)] = e;
                 P.report->iters = iters_after;
                 P.report->status = fin;
+                S->carry.fin_at = k + 1;
+            }
+            if (ONE_STEP) {
+                LookCarry *c = &S->carry;
+                c->iters = iters_after;
+                c->bar_n[0] = bar_n[0]; c->bar_n[1] = bar_n[1];
+                c->j = jn; c->j_prev = j; c->p_prev = p; c->w_prev = w;
             }
             __threadfence();
             *reinterpret_cast<volatile unsigned long long *>(&S->decided) =
@@ -533,12 +566,12 @@ __device__ __forceinline__ void persist_look(const PersistArgs &P, const int cta
             S->dbg[2] += (unsigned long long)(tb1 - t4);     // phase B: loads + division + stores issued
             S->dbg[3] += (unsigned long long)(tb2 - tb1);    // phase B: reduce (+ look-grid barrier)
             S->dbg[4] += (unsigned long long)(t5 - tb2);     // publication (fence)
-            if (fin != ST_RUNNING) {
+            if (fin != ST_RUNNING || (ONE_STEP && (k & 63) == 0)) {
                 S->gt1 = global_timer_ns();
                 S->clk1 = (unsigned long long)t5;
             }
         }
-        if (fin != ST_RUNNING) return;
+        if (fin != ST_RUNNING || ONE_STEP) return;
         j_prev = j; p_prev = p; w_prev = w;
         j = jn;
         iters = iters_after;
@@ -774,8 +807,69 @@ template <int UNROLL, bool STREAM>
 __global__ void __launch_bounds__(kPivotThreads, 2) k_persist(const __grid_constant__ PersistArgs P)
 {
     const int G = P.look_ctas;
-    if ((int)blockIdx.x < G) persist_look(P, blockIdx.x, G);
+    if ((int)blockIdx.x < G) persist_look<false>(P, blockIdx.x, G, 1);
     else persist_tiles<UNROLL, STREAM>(P, (int)blockIdx.x - G, (int)gridDim.x - G);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_iter2: the per-pivot packaging (one launch per pivot, PDL) with the look role of this file:
+// launch L applies pivot L (update tiles, one CTA per 16-row tile -- the hardware CTA scheduler
+// balances the SMs) while its look CTAs take decision L + 1 in two phases on the compact
+// objective-row / RHS copies.  Sharded, the candidates travel the k_persist way: every rank
+// pushes header + scaled candidate row to every rank, one flag wait per pivot.
+// ------------------------------------------------------------------------------------------------
+template <int TR, int UNROLL, bool STREAM>
+__global__ void __launch_bounds__(kPivotThreads, 2)
+k_iter2(const __grid_constant__ PersistArgs P, const long long L)
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
+    PSync *S = P.sync;
+    const int G = P.look_ctas;
+    {
+        // look CTAs only (the tiles judge by their decision record): fin_at = f means decisions
+        // 1..f-1 are pivots to apply and decision f is the verdict -- nothing left to decide
+        if ((int)blockIdx.x < G) {
+            if (*reinterpret_cast<const volatile long long *>(&S->carry.fin_at) != 0) return;
+            if (*reinterpret_cast<const volatile int *>(&S->abort)) return;
+        }
+    }
+    if ((int)blockIdx.x < G) {
+        persist_look<true>(P, blockIdx.x, G, L + 1);
+        return;
+    }
+    if (L == 0) return;                                            // nothing decided yet
+    // One memory round trip before the tile's own loads: the decision record, the 16 pivot-column
+    // values and the thread's slice of the pivot row are all requested together.  Plain (L1-cached)
+    // loads are safe here -- everything was written by an earlier launch and L1 starts empty -- and
+    // let the CTAs that share an SM share the pivot-row lines.
+    __shared__ double s_col[TR];
+    const int slot = (int)((L + P.slot_base) & (kRing - 1));
+    const IterState *st = P.ring + slot;
+    const int st_status = st->status, st_p = st->p, st_w = st->w;
+    const long long st_iters = st->iters;
+    const int ldv = (int)(P.ld >> 1);
+    const int tiles_x = (ldv + kPivotThreads - 1) / kPivotThreads;
+    const int tile = (int)blockIdx.x - G;
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int r_begin = ty * TR;
+    const int r_end = min(P.R_local, r_begin + TR);
+    const double *col = P.colring + (int64_t)slot * P.col_stride;
+    for (int t = threadIdx.x; t < TR; t += kPivotThreads)
+        s_col[t] = (r_begin + t < r_end) ? col[r_begin + t] : 0.0;
+    // a slot that still holds the decision of four launches ago (the solve ended, or was aborted)
+    // is told apart by its pivot count
+    const bool go = st_status == ST_RUNNING && st_p >= 0 && st_iters == P.iters0 + L - 1;
+    if (!go) return;
+    const int rel = st_p - P.row0;
+    const int p_local = (rel >= 0 && rel < P.m_local) ? rel : -1;
+    const double *prow = p_prow(P, slot, st_w);
+    const int cv = tx * kPivotThreads + threadIdx.x;
+    const double2 pr = (cv < ldv) ? *reinterpret_cast<const double2 *>(prow + 2 * cv) : make_double2(0.0, 0.0);
+    __syncthreads();
+    update_tile<TR, UNROLL, STREAM>(reinterpret_cast<const double2 *>(P.tab[(L - 1) & 1]),
+                                    reinterpret_cast<double2 *>(P.tab[L & 1]), ldv, cv, pr, r_begin,
+                                    r_end, p_local, s_col);
 }
 
 } // namespace b200lp

@@ -142,6 +142,8 @@ struct Shard {
     int coop = 0;               // cudaDevAttrCooperativeLaunch
     int sm_count = 0;
     int plook_ctas = 1;
+    PersistArgs pargs;          // arguments of the current b200lp_iterate call (k_iter2)
+    int iter2_ctas = 0;
 };
 
 } // namespace b200lp
@@ -170,6 +172,7 @@ struct b200lp_solver {
     unsigned long long spin_timeout_ns = 20ull * 1000 * 1000 * 1000;    // B200LP_SPIN_TIMEOUT_MS
     unsigned long long ring_base = 0;   // decisions published so far (persistent loop's ring position)
     int last_loop = 0;                  // 1 = k_iter per pivot, 2 = k_persist
+    bool cur_look2 = false;             // this call's per-pivot launches are k_iter2 (look role of persist.cuh)
 };
 
 namespace b200lp {
@@ -196,6 +199,7 @@ static void shape_shard(Shard &sh)
     // barriers) when the rows are short
     sh.look_ctas = sh.ld <= 4096 ? 1 : (int)std::min<int64_t>(kLookMaxCtas, (sh.ld + 1023) / 1024);
     sh.iter_ctas = 0;
+    sh.iter2_ctas = 0;
     sh.ratio_blocks = (sh.R_local + kRatioThreads - 1) / kRatioThreads;
     sh.xchg.ld = sh.ld;
     // persistent loop: one look CTA while a row is short (no look-grid barriers at all), else
@@ -626,6 +630,8 @@ static void launch_update(b200lp_solver *s, Shard &sh, long long k)
     s->kernel_launches++;
 }
 
+static int launch_iter2(b200lp_solver *s, Shard &sh, long long k);   // k_iter2, defined with the persistent loop below
+
 // One fused iteration kernel on every local shard: update(k) || look(k -> k+1) (+ in-kernel exchange).
 static int enqueue_iter(b200lp_solver *s, long long k, long long cap, bool time_pivot)
 {
@@ -643,7 +649,8 @@ static int enqueue_iter(b200lp_solver *s, long long k, long long cap, bool time_
             }
             CU_TRY(cudaEventRecord(sh.ev_pivot[s->ev_used], sh.stream));
         }
-        RC_TRY(launch_iter(s, sh, k, cap));
+        if (s->cur_look2) RC_TRY(launch_iter2(s, sh, k));
+        else RC_TRY(launch_iter(s, sh, k, cap));
         if (timed) {
             CU_TRY(cudaEventRecord(sh.ev_pivot[s->ev_used + 1], sh.stream));
             s->ev_used += 2;
@@ -770,6 +777,87 @@ static bool want_persist(const b200lp_solver *s)
     return true;
 }
 
+// phase sums are SM cycles; the (%globaltimer, clock64) pairs of the call convert them
+static void fill_look_telemetry(const PSync &ps, b200lp_result *out)
+{
+    double ns_per_cycle = 0.52;                            // ~1.92 GHz when the call was too short to tell
+    if (ps.clk1 > ps.clk0 && ps.gt1 > ps.gt0 && ps.gt1 - ps.gt0 > 20000)
+        ns_per_cycle = (double)(ps.gt1 - ps.gt0) / (double)(ps.clk1 - ps.clk0);
+    const double cyc_ms = ns_per_cycle * 1e-6;
+    out->ms_look_kernel = (double)(ps.ns_wait_done + ps.ns_a + ps.ns_b1 + ps.ns_xwait + ps.ns_b2) * cyc_ms;
+    out->look_kernel_launches = (int64_t)ps.look_count;
+    out->ms_look_wait = (double)ps.ns_wait_done * cyc_ms;
+    out->ms_look_ratio = (double)ps.ns_a * cyc_ms;
+    out->ms_look_push = (double)ps.ns_b1 * cyc_ms;
+    out->ms_look_peer_wait = (double)ps.ns_xwait * cyc_ms;
+    out->ms_look_row = (double)ps.ns_b2 * cyc_ms;
+    out->sm_clock_mhz = 1e3 / ns_per_cycle;
+    for (int q = 0; q < 8; ++q) out->ms_look_dbg[q] = (double)ps.dbg[q] * cyc_ms;
+}
+
+static void fill_pargs(b200lp_solver *s, Shard &sh, long long start_iters, long long cap, PersistArgs *pa)
+{
+    PersistArgs &a = *pa;
+    std::memset(&a, 0, sizeof(a));
+    a.tab[0] = sh.tabs[sh.cur]; a.tab[1] = sh.tabs[sh.cur ^ 1];
+    a.ld = sh.ld;
+    a.C = (int)s->C; a.m_local = sh.m_local; a.R_local = sh.R_local; a.row0 = (int)sh.row0;
+    a.world = s->world; a.rank = sh.rank; a.is_max = s->is_max; a.rule = s->opts.pivot_rule;
+    a.mode = s->xmode;
+    a.thr_enter = s->thr_enter; a.thr_pivot = s->thr_pivot;
+    a.iters0 = start_iters; a.max_iters = cap;
+    a.ring = sh.ring; a.colring = sh.colring; a.col_stride = sh.R_local;
+    a.prowring = sh.candring + kCandHdr; a.prow_stride = kCandHdr + sh.ld;
+    a.objc = sh.objc; a.rhsc = sh.rhsc;
+    a.xchg = sh.xchg; a.xchg.epoch = s->epoch;
+    a.basis = sh.basis; a.report = sh.report;
+    a.trace = sh.trace; a.trace_cap = s->opts.trace_capacity;
+    a.sync = sh.psync;
+    a.timeout_ns = s->world > 1 ? std::max(s->peer_timeout_ns, s->spin_timeout_ns) : s->spin_timeout_ns;
+    a.look_ctas = sh.plook_ctas;
+    a.slot_base = (int)(s->ring_base & (kRing - 1));
+    a.rates = getenv("B200LP_NO_BALANCE") ? nullptr : sh.rates;
+}
+
+// k_iter2: per-pivot launches with the two-phase look role of persist.cuh.  B200LP_LOOK=1 keeps
+// the round-1 look role (k_iter).
+static bool want_look2(const b200lp_solver *s)
+{
+    if (s->xmode == 1) return false;
+    const char *e = getenv("B200LP_LOOK");
+    return !(e && e[0] == '1');
+}
+
+template <int TR, int UNROLL, bool STREAM>
+static cudaError_t launch_iter2_t(Shard &sh, long long k)
+{
+    if (sh.iter2_ctas == 0) {
+        const int64_t ldv = sh.ld / 2;
+        const int64_t ntiles = ((ldv + kPivotThreads - 1) / kPivotThreads) * ((sh.R_local + TR - 1) / TR);
+        sh.iter2_ctas = sh.pargs.look_ctas + (int)ntiles;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)sh.iter2_ctas);
+    cfg.blockDim = dim3(kPivotThreads);
+    cfg.stream = sh.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_iter2<TR, UNROLL, STREAM>, sh.pargs, k);
+}
+
+static int launch_iter2(b200lp_solver *s, Shard &sh, long long k)
+{
+    const int v = pick_variant(s, sh);
+#define X(TR, UN, ST) CU_TRY((launch_iter2_t<TR, UN, ST>(sh, k)))
+    B200LP_VARIANTS(X)
+#undef X
+    s->kernel_launches++;
+    return B200LP_OK;
+}
+
 template <int UNROLL, bool STREAM>
 static cudaError_t launch_persist_t(Shard &sh, PersistArgs &a)
 {
@@ -811,25 +899,7 @@ static int iterate_persist(b200lp_solver *s, int64_t limit, b200lp_result *out, 
     for (Shard &sh : s->shards) {
         CU_TRY(cudaSetDevice(sh.device));
         PersistArgs a;
-        std::memset(&a, 0, sizeof(a));
-        a.tab[0] = sh.tabs[sh.cur]; a.tab[1] = sh.tabs[sh.cur ^ 1];
-        a.ld = sh.ld;
-        a.C = (int)s->C; a.m_local = sh.m_local; a.R_local = sh.R_local; a.row0 = (int)sh.row0;
-        a.world = s->world; a.rank = sh.rank; a.is_max = s->is_max; a.rule = s->opts.pivot_rule;
-        a.mode = s->xmode;
-        a.thr_enter = s->thr_enter; a.thr_pivot = s->thr_pivot;
-        a.iters0 = start_iters; a.max_iters = cap;
-        a.ring = sh.ring; a.colring = sh.colring; a.col_stride = sh.R_local;
-        a.prowring = sh.candring + kCandHdr; a.prow_stride = kCandHdr + sh.ld;
-        a.objc = sh.objc; a.rhsc = sh.rhsc;
-        a.xchg = sh.xchg; a.xchg.epoch = s->epoch;
-        a.basis = sh.basis; a.report = sh.report;
-        a.trace = sh.trace; a.trace_cap = s->opts.trace_capacity;
-        a.sync = sh.psync;
-        a.timeout_ns = s->world > 1 ? std::max(s->peer_timeout_ns, s->spin_timeout_ns) : s->spin_timeout_ns;
-        a.look_ctas = sh.plook_ctas;
-        a.slot_base = (int)(s->ring_base & (kRing - 1));
-        a.rates = getenv("B200LP_NO_BALANCE") ? nullptr : sh.rates;
+        fill_pargs(s, sh, start_iters, cap, &a);
         if (getenv("B200LP_TILE_PROFILE")) {
             if (!sh.tile_prof) CU_TRY(cudaMalloc(&sh.tile_prof, sizeof(unsigned long long) * 2 * 4096));
             CU_TRY(cudaMemsetAsync(sh.tile_prof, 0, sizeof(unsigned long long) * 2 * 4096, sh.stream));
@@ -897,20 +967,7 @@ static int iterate_persist(b200lp_solver *s, int64_t limit, b200lp_result *out, 
         float ms = 0.f;
         CU_TRY(cudaEventElapsedTime(&ms, s0.ev_begin, s0.ev_end));
         out->ms_solve = ms;
-        // phase sums are SM cycles; the (%globaltimer, clock64) pairs of the call convert them
-        double ns_per_cycle = 0.52;                        // ~1.92 GHz when the call was too short to tell
-        if (ps.clk1 > ps.clk0 && ps.gt1 > ps.gt0 && ps.gt1 - ps.gt0 > 20000)
-            ns_per_cycle = (double)(ps.gt1 - ps.gt0) / (double)(ps.clk1 - ps.clk0);
-        const double cyc_ms = ns_per_cycle * 1e-6;
-        out->ms_look_kernel = (double)(ps.ns_wait_done + ps.ns_a + ps.ns_b1 + ps.ns_xwait + ps.ns_b2) * cyc_ms;
-        out->look_kernel_launches = (int64_t)ps.look_count;
-        out->ms_look_wait = (double)ps.ns_wait_done * cyc_ms;
-        out->ms_look_ratio = (double)ps.ns_a * cyc_ms;
-        out->ms_look_push = (double)ps.ns_b1 * cyc_ms;
-        out->ms_look_peer_wait = (double)ps.ns_xwait * cyc_ms;
-        out->ms_look_row = (double)ps.ns_b2 * cyc_ms;
-        out->sm_clock_mhz = 1e3 / ns_per_cycle;
-        for (int q = 0; q < 8; ++q) out->ms_look_dbg[q] = (double)ps.dbg[q] * cyc_ms;
+        fill_look_telemetry(ps, out);
         out->kernel_launches = s->kernel_launches - launches0;
         out->bytes_per_pivot = 16 * (int64_t)s0.R_local * s->C;
         double obj = 0.0;
@@ -952,11 +1009,17 @@ static int iterate_locked(b200lp_solver *s, int64_t limit, b200lp_result *out, i
     s->ev_used = 0;
     s->evl_used = 0;
     const bool fused = s->xmode != 1;
+    s->cur_look2 = fused && want_look2(s);
     s->epoch += 1ull << 40;                                // fresh sequence numbers for this call
     for (Shard &sh : s->shards) {
         CU_TRY(cudaSetDevice(sh.device));
         if (!sh.tabs[1]) CU_TRY(cudaMalloc(&sh.tabs[1], sizeof(double) * sh.cap_ld * sh.cap_rows));
         cudaStream_t st0 = fused ? sh.stream : sh.look_stream;
+        if (s->cur_look2) {
+            fill_pargs(s, sh, start_iters, cap, &sh.pargs);
+            sh.iter2_ctas = 0;
+            CU_TRY(cudaMemsetAsync(sh.psync, 0, sizeof(PSync), st0));
+        }
         IterState init;
         std::memset(&init, 0, sizeof(init));
         init.status = ST_START; init.j = -1; init.p = -1; init.iters = start_iters;
@@ -1046,6 +1109,7 @@ static int iterate_locked(b200lp_solver *s, int64_t limit, b200lp_result *out, i
         return fail(B200LP_ERR_PEER_TIMEOUT, "iterate", "a peer GPU's candidate never arrived");
     const long long done = last.iters - start_iters;
     s->iters_done = last.iters;
+    if (s->cur_look2) s->ring_base += (unsigned long long)done + 1ull;
     for (Shard &sh : s->shards) {                          // pivots ping-pong between the buffers
         sh.cur = (sh.cur + (int)(done & 1)) & 1;
         sh.tab = sh.tabs[sh.cur];
@@ -1058,7 +1122,7 @@ static int iterate_locked(b200lp_solver *s, int64_t limit, b200lp_result *out, i
         out->n_devices = s->world;
         out->exchange_mode = s->xmode;
         out->loop_mode = 1;
-        out->look_ctas = s0.look_ctas;
+        out->look_ctas = s->cur_look2 ? s0.plook_ctas : s0.look_ctas;
         out->iterations = done;
         float ms = 0.f;
         CU_TRY(cudaEventElapsedTime(&ms, s0.ev_begin, s0.ev_end));
@@ -1086,11 +1150,16 @@ static int iterate_locked(b200lp_solver *s, int64_t limit, b200lp_result *out, i
         out->ms_look_kernel = lk;
         out->ms_exchange = xk;
         out->look_kernel_launches = (int64_t)real_l;
-        if (fused) {                                       // timed on the device by the look role
+        if (fused && !s->cur_look2) {                      // timed on the device by the look role
             LookSync ls;
             CU_TRY(cudaMemcpy(&ls, s0.look_sync, sizeof(ls), cudaMemcpyDeviceToHost));
             out->ms_look_kernel = (double)ls.look_ns * 1e-6;
             out->look_kernel_launches = ls.look_count;
+        }
+        if (s->cur_look2) {
+            PSync ps;
+            CU_TRY(cudaMemcpy(&ps, s0.psync, sizeof(ps), cudaMemcpyDeviceToHost));
+            fill_look_telemetry(ps, out);
         }
         out->kernel_launches = s->kernel_launches - launches0;
         out->bytes_per_pivot = 16 * (int64_t)s0.R_local * s->C;

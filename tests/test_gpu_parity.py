@@ -229,6 +229,28 @@ def test_every_pivot_kernel_variant_is_bit_exact(variant):
     assert res.loop_mode == (2 if variant >= 20 else 1)
 
 
+@pytest.mark.parametrize("look", ["1", "2"], ids=["round-1-look-role", "two-phase-look-role"])
+@pytest.mark.parametrize("look_ctas", [1, 3, 16])
+@pytest.mark.parametrize("m,n,rule", [(700, 3500, 0), (90, 5000, 1), (3000, 200, 0)])
+def test_per_pivot_loop_both_look_roles_bit_exact(m, n, rule, look_ctas, look, monkeypatch):
+    """One launch per pivot (variant 10) with either look role: k_iter (round 1: three stages, the
+    objective row re-read from the tableau) and k_iter2 (persist.cuh's two phases on compact
+    copies, one decision per launch, state carried between launches)."""
+    monkeypatch.setenv("B200LP_LOOK", look)
+    monkeypatch.setenv("B200LP_LOOK_CTAS", str(look_ctas))
+    tab, basis = random_tableau(m, n, seed=m + n, signed=True)
+    o_tab, o_basis = tab.copy(), basis.copy()
+    cap = 600
+    ost, oit, otrace = oracle.solve(o_tab, o_basis, True, rule=rule, max_iters=cap, trace_cap=cap,
+                                    parallel=True)
+    st, res, trace = _ffi.solve(tab, basis, True,
+                                _ffi.make_opts(pivot_rule=rule, max_iters=cap, trace_capacity=cap,
+                                               writeback_full=True, pivot_variant=10))
+    assert (st, res.iterations) == (ost, oit) and trace == otrace
+    assert res.loop_mode == 1
+    assert np.array_equal(basis, o_basis) and np.array_equal(tab, o_tab)
+
+
 @pytest.mark.parametrize("look_ctas", [1, 2, 5, 16])
 @pytest.mark.parametrize("m,n,rule", [(700, 3500, 0), (90, 5000, 1), (3000, 200, 0)])
 def test_persistent_loop_any_look_grid_is_bit_exact(m, n, rule, look_ctas, monkeypatch):
