@@ -362,7 +362,10 @@ def run_b200(args, cfg, workload):
     bytes_per_launch = int(res.bytes_per_pivot)
     loop_mode = int(res.loop_mode)
     value = steps_done / (ms_total / 1e3)
-    ms_look = max_over_ranks(res.ms_look_kernel / max(res.look_kernel_launches, 1))
+    n_look = max(res.look_kernel_launches, 1)
+    ms_look = max_over_ranks(res.ms_look_kernel / n_look)
+    look_split = {k: max_over_ranks(1e3 * getattr(res, "ms_look_" + k) / n_look)
+                  for k in ("wait", "ratio", "push", "peer_wait", "row")}
     ms_pivot_isolated = None
     ms_exch = 0.0
     if loop_mode == 1:
@@ -537,7 +540,9 @@ def run_b200(args, cfg, workload):
             "overlapped": {"what": "lookahead CTAs (entering column, ratio test, pivot-row scaling and, "
                                    "sharded, the candidate exchange) run inside the same launch, "
                                    "concurrently with the update tiles",
-                           "ms_look": ms_look, "ms_exchange_nccl_fallback": ms_exch},
+                           "ms_look": ms_look, "look_ctas": int(res.look_ctas),
+                           "us_look_split_max_over_ranks": look_split,
+                           "ms_exchange_nccl_fallback": ms_exch},
             "parity": parity, "cfg4": cfg4, "build_tableau": build_info, "mps": mps_info,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }

@@ -149,13 +149,17 @@ __device__ __forceinline__ bool cta_wait_ge(const unsigned long long *p, unsigne
 }
 
 // Barrier of the G look CTAs (co-resident: cooperative launch).  `target` = G x (uses so far).
+// `sys`: the writes being published went to peer GPUs (system scope).  One fence by thread 0 after
+// the CTA barrier covers the whole CTA's writes (cumulativity) -- a membar.sys per thread, thousands
+// per pivot, measurably slows the update tiles running beside the look CTAs.
 __device__ __forceinline__ bool look_bar(PSync *S, int which, unsigned long long target,
-                                         unsigned long long timeout_ns)
+                                         unsigned long long timeout_ns, const bool sys = false)
 {
     __syncthreads();
     int ok = 1;
     if (threadIdx.x == 0) {
-        __threadfence();
+        if (sys) __threadfence_system();
+        else __threadfence();
         atomicAdd(&S->bar[which], 1ull);
         ok = spin_ge(&S->bar[which], target, S, timeout_ns, ST_SPIN_TIMEOUT) ? 1 : 0;
     }
@@ -438,12 +442,13 @@ __device__ __forceinline__ void persist_look(const PersistArgs &P, const int cta
                             *reinterpret_cast<double2 *>(P.xchg.peer[g] + off + 2 * v) = x;
                     }
                 }
-                __threadfence_system();
             }
             if (G > 1) {                                           // every CTA's slice is on its way
                 bar_n[1] += G;
-                if (!look_bar(S, 1, bar_n[1], P.timeout_ns)) return;
+                if (!look_bar(S, 1, bar_n[1], P.timeout_ns, /*sys=*/true)) return;
             } else {
+                __syncthreads();
+                if (tid == 0) __threadfence_system();
                 __syncthreads();
             }
             if (cta == 0 && tid < P.world) {
