@@ -32,7 +32,7 @@ CONFIGS = {
     "cfg2": dict(m=1024, n=2048, degenerate=False),
     "cfg3": dict(m=8192, n=16384, degenerate=False),
     "cfg4": dict(m=16384, n=32768, degenerate=False),
-    "cfg5": dict(m=4096, n=4096, degenerate=True),
+    "cfg5": dict(m=4096, n=4096, degenerate=True, zero_frac=1 / 64),   # 64 cone rows: solves in 53 616 pivots
 }
 METRIC = "simplex_pivots_per_sec"
 UNIT = "pivots/s"
@@ -138,7 +138,7 @@ def run_reference(args, cfg, workload):
     from oracle import oracle
     oracle.build()
     m, n = cfg["m"], cfg["n"]
-    tab, basis = synthetic.dense_tableau(m, n, degenerate=cfg["degenerate"])
+    tab, basis = synthetic.dense_tableau(m, n, degenerate=cfg["degenerate"], zero_frac=cfg.get("zero_frac", 0.5))
     R, C = tab.shape
     cores = oracle.set_num_threads(len(os.sched_getaffinity(0)))
     budget_s = 150.0
@@ -315,7 +315,7 @@ def run_b200(args, cfg, workload):
         # f2: the fp64 tableau is written straight into it (no boxed intermediate, no second pass)
         host = torch.empty((R, C), dtype=torch.float64, pin_memory=True)
         tab = host.numpy()
-        A, bvec, cvec = synthetic.dense_lp(m, n, degenerate=cfg["degenerate"])
+        A, bvec, cvec = synthetic.dense_lp(m, n, degenerate=cfg["degenerate"], zero_frac=cfg.get("zero_frac", 0.5))
         t0 = time.perf_counter()
         _, basis = synthetic.tableau_from_lp(A, bvec, cvec, out=tab)
         t_build = time.perf_counter() - t0
@@ -474,7 +474,8 @@ def run_b200(args, cfg, workload):
         from oracle import oracle
         oracle.build()
         oracle.set_num_threads(len(os.sched_getaffinity(0)))
-        tab2, basis2 = synthetic.dense_tableau(m, n, degenerate=cfg["degenerate"], out=tab)
+        tab2, basis2 = synthetic.dense_tableau(m, n, degenerate=cfg["degenerate"], out=tab,
+                                                zero_frac=cfg.get("zero_frac", 0.5))
         n_cpu, t_budget = 0, 20.0
         for k in range(2):   # warm-up
             j = oracle.find_entering_column(tab2, True)

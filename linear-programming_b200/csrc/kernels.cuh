@@ -372,6 +372,7 @@ k_pivot(double *__restrict__ tab, int64_t ld, int m_local, int R_local, int row0
 // ==========================================================================================
 constexpr int ST_START = 101;            // ring slot holds no pending pivot (first look of a call)
 constexpr int ST_PEER_TIMEOUT = -7;      // == B200LP_ERR_PEER_TIMEOUT
+constexpr int ST_BARRIER_TIMEOUT = -6;   // == B200LP_ERR_INTERNAL: a look-grid barrier gave up
 constexpr int kRing = 4;
 constexpr int kLookThreads = 256;        // == kPivotThreads: both roles share k_iter's CTA shape
 constexpr int kLookMaxCtas = 32;
@@ -481,13 +482,22 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
 // Grid-wide barrier of the G look CTAs (co-resident by construction: the lowest block indices
 // of k_iter, or a small grid on a high-priority stream).  Data written before it is visible
 // after it to loads that bypass L1.
-__device__ __forceinline__ void look_barrier(unsigned int *ctr, int G)
+// The spin is bounded (SM cycle counter, 2 cycles per ns of `timeout_ns`): should the CTAs ever
+// not be co-resident (MPS, a debugger, a scheduler that dispatches differently) the wait gives up,
+// raises bit 1 of *fail and the call ends with B200LP_ERR_INTERNAL instead of hanging the GPU.
+__device__ __forceinline__ void look_barrier(unsigned int *ctr, int G, unsigned int *fail,
+                                             unsigned long long timeout_ns)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(ctr, 1u);
-        while (*reinterpret_cast<volatile unsigned int *>(ctr) < (unsigned)G) { }
+        const long long t0 = clock64();
+        const long long budget = (long long)(timeout_ns << 1);
+        while (*reinterpret_cast<volatile unsigned int *>(ctr) < (unsigned)G) {
+            if (*reinterpret_cast<volatile unsigned int *>(fail) & 2u) break;
+            if (clock64() - t0 > budget) { atomicOr(fail, 2u); break; }
+        }
         __threadfence();
     }
     __syncthreads();
@@ -627,7 +637,7 @@ __device__ __forceinline__ void look_role(const LookArgs &A, const int cta, cons
         best = cand_block_min<kLookThreads>(best, red);
         if (G > 1) {
             if (tid == 0) A.sync->part_enter[cta] = best;
-            look_barrier(&A.sync->bar[0], G);
+            look_barrier(&A.sync->bar[0], G, &A.sync->fail, A.timeout_ns);
             best = look_reduce_partials(A.sync->part_enter, G, &s_part);
         }
         const bool accept = (best.row >= 0) && (A.rule != 0 || best.q < 0.0 - A.thr_enter);
@@ -678,7 +688,7 @@ __device__ __forceinline__ void look_role(const LookArgs &A, const int cta, cons
         c = cand_block_min<kLookThreads>(c, red);
         if (G > 1) {
             if (tid == 0) A.sync->part_ratio[cta] = c;
-            look_barrier(&A.sync->bar[1], G);
+            look_barrier(&A.sync->bar[1], G, &A.sync->fail, A.timeout_ns);
             c = look_reduce_partials(A.sync->part_ratio, G, &s_part);
         }
         // c = this shard's best (ratio, key, row)
@@ -774,7 +784,8 @@ __device__ __forceinline__ void look_role(const LookArgs &A, const int cta, cons
     if (!s_last) return;
     if (tid == 0) {
         __threadfence();
-        if (A.sync->fail) fin = ST_PEER_TIMEOUT;
+        if (A.sync->fail & 2u) fin = ST_BARRIER_TIMEOUT;
+        else if (A.sync->fail) fin = ST_PEER_TIMEOUT;
         A.sync->bar[0] = 0; A.sync->bar[1] = 0; A.sync->bar[2] = 0; A.sync->fail = 0;
         s_ok = 1;
     }

@@ -823,6 +823,16 @@ __global__ void __launch_bounds__(kPivotThreads, 2) k_persist(const __grid_const
 // objective-row / RHS copies.  Sharded, the candidates travel the k_persist way: every rank
 // pushes header + scaled candidate row to every rank, one flag wait per pivot.
 // ------------------------------------------------------------------------------------------------
+// A wait of an earlier launch timed out (PSync::abort): the first look thread of the next launch
+// turns that into the verdict the host is polling for, and nothing else runs.
+__device__ __forceinline__ bool piter2_aborted(const PersistArgs &P)
+{
+    const int a = *reinterpret_cast<const volatile int *>(&P.sync->abort);
+    if (a == 0) return false;
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.report->status = a;
+    return true;
+}
+
 template <int TR, int UNROLL, bool STREAM>
 __global__ void __launch_bounds__(kPivotThreads, 2)
 k_iter2(const __grid_constant__ PersistArgs P, const long long L)
@@ -836,7 +846,7 @@ k_iter2(const __grid_constant__ PersistArgs P, const long long L)
         // 1..f-1 are pivots to apply and decision f is the verdict -- nothing left to decide
         if ((int)blockIdx.x < G) {
             if (*reinterpret_cast<const volatile long long *>(&S->carry.fin_at) != 0) return;
-            if (*reinterpret_cast<const volatile int *>(&S->abort)) return;
+            if (piter2_aborted(P)) return;
         }
     }
     if ((int)blockIdx.x < G) {
@@ -875,6 +885,123 @@ k_iter2(const __grid_constant__ PersistArgs P, const long long L)
     update_tile<TR, UNROLL, STREAM>(reinterpret_cast<const double2 *>(P.tab[(L - 1) & 1]),
                                     reinterpret_cast<double2 *>(P.tab[L & 1]), ldv, cv, pr, r_begin,
                                     r_end, p_local, s_col);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_iter2_bulk: the same launch with the update tile staged through shared memory by the bulk
+// asynchronous copy engine (TMA's 1-D form): one elected thread issues cp.async.bulk for the
+// tile's row segments global -> shared (completion counted in bytes on an mbarrier), every thread
+// updates its 16-byte column slice in place in shared memory, and the tile goes back with
+// cp.async.bulk shared -> global.  No registers hold data in flight (3 CTAs x 64 KB per SM instead
+// of 2 CTAs x 16 loads x 16 B x 256 threads).  SASS: UBLKCP (both directions), SYNCS (mbarrier).
+// The A/B against the LDG/STG tile is in profiles/ (variant 30 vs 10); see DESIGN.md.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBulkRows = 16;
+constexpr int kBulkRowBytes = kPivotThreads * 16;      // 4 KB: one row segment of a tile
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+template <bool STREAM>
+__global__ void __launch_bounds__(kPivotThreads, 3)
+k_iter2_bulk(const __grid_constant__ PersistArgs P, const long long L)
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
+    PSync *S = P.sync;
+    const int G = P.look_ctas;
+    if ((int)blockIdx.x < G) {
+        if (*reinterpret_cast<const volatile long long *>(&S->carry.fin_at) != 0) return;
+        if (piter2_aborted(P)) return;
+        persist_look<true>(P, blockIdx.x, G, L + 1);
+        return;
+    }
+    if (L == 0) return;
+    extern __shared__ __align__(128) unsigned char bulk_smem[];   // kBulkRows x 4 KB
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ double s_col[kBulkRows];
+    const int slot = (int)((L + P.slot_base) & (kRing - 1));
+    const IterState *st = P.ring + slot;
+    const int st_status = st->status, st_p = st->p, st_w = st->w;
+    const long long st_iters = st->iters;
+    const bool go = st_status == ST_RUNNING && st_p >= 0 && st_iters == P.iters0 + L - 1;
+    if (!go) return;
+    const int ldv = (int)(P.ld >> 1);
+    const int tiles_x = (ldv + kPivotThreads - 1) / kPivotThreads;
+    const int tile = (int)blockIdx.x - G;
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int r_begin = ty * kBulkRows;
+    const int rows = min(P.R_local, r_begin + kBulkRows) - r_begin;
+    const int width = min(kPivotThreads, ldv - tx * kPivotThreads);       // double2 columns in this tile
+    const uint32_t row_bytes = (uint32_t)width * 16u;                      // multiple of 128
+    const double *src = P.tab[(L - 1) & 1];
+    double *dst = P.tab[L & 1];
+    const int64_t col0 = (int64_t)tx * kPivotThreads * 2;                  // first double column
+    const uint32_t bar = smem_u32(&s_bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                     "r"(row_bytes * (uint32_t)rows) : "memory");
+        for (int r = 0; r < rows; ++r) {
+            const double *g = src + (int64_t)(r_begin + r) * P.ld + col0;
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                ::"r"(smem_u32(bulk_smem + (size_t)r * kBulkRowBytes)), "l"(g), "r"(row_bytes), "r"(bar)
+                : "memory");
+        }
+    }
+    const double *col = P.colring + (int64_t)slot * P.col_stride;
+    for (int t = threadIdx.x; t < kBulkRows; t += kPivotThreads)
+        s_col[t] = (t < rows) ? col[r_begin + t] : 0.0;
+    const int rel = st_p - P.row0;
+    const int p_local = (rel >= 0 && rel < P.m_local) ? rel : -1;
+    const double *prow = p_prow(P, slot, st_w);
+    const int cv = tx * kPivotThreads + threadIdx.x;
+    const bool act = (int)threadIdx.x < width;
+    const double2 pr = act ? *reinterpret_cast<const double2 *>(prow + 2 * cv) : make_double2(0.0, 0.0);
+    __syncthreads();                                   // s_col; the barrier is initialised for everyone
+    {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+        }
+    }
+    if (act) {
+        double2 *tilev = reinterpret_cast<double2 *>(bulk_smem);
+#pragma unroll
+        for (int r = 0; r < kBulkRows; ++r) {
+            if (r < rows) {
+                double2 *cell = tilev + r * kPivotThreads + threadIdx.x;
+                const double2 a = *cell;
+                const double t = s_col[r];
+                double2 o;
+                o.x = __dsub_rn(a.x, __dmul_rn(t, pr.x));
+                o.y = __dsub_rn(a.y, __dmul_rn(t, pr.y));
+                if (r_begin + r == p_local) o = pr;
+                *cell = o;
+            }
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> async proxy reads
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int r = 0; r < rows; ++r) {
+            double *g = dst + (int64_t)(r_begin + r) * P.ld + col0;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(g), "r"(smem_u32(bulk_smem + (size_t)r * kBulkRowBytes)), "r"(row_bytes)
+                         : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory may go once it is read
+    }
+    (void)STREAM;
 }
 
 } // namespace b200lp

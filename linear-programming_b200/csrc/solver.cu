@@ -770,6 +770,7 @@ static bool want_persist(const b200lp_solver *s)
     for (const Shard &sh : s->shards)
         if (!sh.coop) return false;
     const int v = s->opts.pivot_variant;
+    if (v == 30) return false;                      // k_iter2_bulk: a per-pivot launch
     if (v >= 20 || loop_env() == 2) return true;
     if (v >= 1) return false;
     for (const Shard &sh : s->shards)
@@ -848,8 +849,38 @@ static cudaError_t launch_iter2_t(Shard &sh, long long k)
     return cudaLaunchKernelEx(&cfg, k_iter2<TR, UNROLL, STREAM>, sh.pargs, k);
 }
 
+// variant 30: the update tile staged by the bulk asynchronous copy engine (k_iter2_bulk)
+static int launch_iter2_bulk(b200lp_solver *s, Shard &sh, long long k)
+{
+    static bool attr_set = false;
+    const int smem = kBulkRows * kBulkRowBytes;
+    if (!attr_set) {
+        CU_TRY(cudaFuncSetAttribute(k_iter2_bulk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    if (sh.iter2_ctas == 0) {
+        const int64_t ldv = sh.ld / 2;
+        const int64_t ntiles = ((ldv + kPivotThreads - 1) / kPivotThreads) * ((sh.R_local + kBulkRows - 1) / kBulkRows);
+        sh.iter2_ctas = sh.pargs.look_ctas + (int)ntiles;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)sh.iter2_ctas);
+    cfg.blockDim = dim3(kPivotThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = sh.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CU_TRY(cudaLaunchKernelEx(&cfg, k_iter2_bulk<true>, sh.pargs, k));
+    s->kernel_launches++;
+    return B200LP_OK;
+}
+
 static int launch_iter2(b200lp_solver *s, Shard &sh, long long k)
 {
+    if (s->opts.pivot_variant == 30) return launch_iter2_bulk(s, sh, k);
     const int v = pick_variant(s, sh);
 #define X(TR, UN, ST) CU_TRY((launch_iter2_t<TR, UN, ST>(sh, k)))
     B200LP_VARIANTS(X)
@@ -1107,6 +1138,20 @@ static int iterate_locked(b200lp_solver *s, int64_t limit, b200lp_result *out, i
         return fail(B200LP_ERR_INTERNAL, "iterate", "device loop ended without a verdict");
     if (last.status == ST_PEER_TIMEOUT)
         return fail(B200LP_ERR_PEER_TIMEOUT, "iterate", "a peer GPU's candidate never arrived");
+    if (last.status == ST_BARRIER_TIMEOUT)
+        return fail(B200LP_ERR_INTERNAL, "iterate", "a barrier of the look CTAs timed out");
+    if (s->cur_look2) {                                    // k_iter2: an aborted wait leaves no verdict
+        for (Shard &sh : s->shards) {
+            PSync q;
+            CU_TRY(cudaSetDevice(sh.device));
+            CU_TRY(cudaMemcpy(&q, sh.psync, sizeof(q), cudaMemcpyDeviceToHost));
+            if (q.abort == ST_PEER_TIMEOUT)
+                return fail(B200LP_ERR_PEER_TIMEOUT, "iterate", "a peer GPU's candidate never arrived");
+            if (q.abort)
+                return fail(B200LP_ERR_INTERNAL, "iterate", "a wait of the look CTAs timed out");
+        }
+        CU_TRY(cudaSetDevice(s0.device));
+    }
     const long long done = last.iters - start_iters;
     s->iters_done = last.iters;
     if (s->cur_look2) s->ring_base += (unsigned long long)done + 1ull;

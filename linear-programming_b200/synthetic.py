@@ -14,8 +14,13 @@ def dense_lp(m, n, seed=1234, degenerate=False, zero_frac=0.5):
     the rows are cone constraints through the origin (A in {-1,0,1}, b = 0: every ratio there
     is exactly 0, so the leaving row is decided by the tie-break alone); the second half
     (A in {0,1,2}, b in {n/4, n/2, 3n/4}) bounds the polytope; c in {1,2,3}.  `zero_frac` is the
-    share of cone rows: 1/2 stalls for millions of pivots at m = 4096 (prefix-parity use), 1/32 still
-    produces thousands of exact ties but solves in ~10^4 pivots."""
+    share of cone rows.  Measured with the oracle's cycle probe (tools/cfg5_probe.py; DESIGN.md
+    section 2): neither rule ever revisits a basis on this family -- the reference rule STALLS, it
+    does not cycle -- and the length of the stall grows steeply with the number of cone rows:
+    zero_frac 1/2 at m = 4096 is still at objective 0 after 3 * 10^6 pivots under either rule
+    (prefix-parity use only), while zero_frac 1/64 (64 cone rows, the instance bench.py and the
+    full-size parity fixture call config 5) solves in 53 616 pivots under the reference rule.
+    Bland's rule is slow on the whole family (about m^2.6 pivots: 177 000 at m = 1024)."""
     rng = np.random.default_rng(seed)
     if degenerate:
         A = rng.integers(0, 3, size=(m, n)).astype(np.float64)

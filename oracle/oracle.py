@@ -55,6 +55,10 @@ def lib():
             _c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _c_int32_p,
             ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int64, ctypes.c_int,
             _c_int64_p, _c_int32_p, _c_int32_p, ctypes.c_int64]
+        L.oracle_solve_cycle_probe.restype = ctypes.c_int
+        L.oracle_solve_cycle_probe.argtypes = [
+            _c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _c_int32_p,
+            ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int64, ctypes.c_int, _c_int64_p]
         L.oracle_solve_two_phase.restype = ctypes.c_int
         L.oracle_solve_two_phase.argtypes = [
             _c_double_p, ctypes.c_int64, ctypes.c_int64, _c_int32_p,
@@ -121,6 +125,17 @@ def solve(tab, basis, is_max=True, tol=1024.0, rule=0, max_iters=0, parallel=Fal
                             _ip(tj), _ip(tr), trace_cap)
     n = min(iters.value, trace_cap)
     return st, iters.value, list(zip(tj[:n].tolist(), tr[:n].tolist()))
+
+
+def solve_cycle_probe(tab, basis, is_max=True, tol=1024.0, rule=0, max_iters=100000, parallel=False):
+    """n-solve-tableau in place with a basis-revisit detector (a revisited basis under a
+    deterministic rule is a proven cycle).  Returns (status, dict(pivots, degenerate_pivots,
+    revisit_at, first_visit_at)); revisit_at is -1 when no basis was seen twice."""
+    R, C, ld = _check_tab(tab)
+    out = (ctypes.c_int64 * 4)()
+    st = lib().oracle_solve_cycle_probe(_dp(tab), R, C, ld, _ip(basis), int(is_max), tol, rule,
+                                        max_iters, int(parallel), out)
+    return st, dict(pivots=out[0], degenerate_pivots=out[1], revisit_at=out[2], first_visit_at=out[3])
 
 
 def solve_two_phase(art, art_basis, main, main_basis, is_max=True, tol=1024.0, rule=0,

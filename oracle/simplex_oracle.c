@@ -275,3 +275,56 @@ int oracle_solve_two_phase(double *art, int64_t C_art, int64_t ld_art, int32_t *
     if (iters_out) iters_out[2] = it2;
     return st;
 }
+
+/* n-solve-tableau with a cycle probe (config 5's question: does the reference rule CYCLE on a
+ * degenerate LP, or merely stall?).  The reference has no anti-cycling (src/simplex.lisp:455-460),
+ * so a revisited basis -- the same column basic in the same row, for every row -- under a
+ * deterministic rule is a proven cycle.  The basis vector is hashed incrementally (one term per
+ * row, replaced on every pivot); hashes live in an open-addressing table sized for max_iters.
+ * out[0] = pivots done, out[1] = degenerate pivots (objective value unchanged), out[2] = pivot
+ * index at which a basis was first revisited (-1: never), out[3] = pivot index of its first visit. */
+static uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+
+int oracle_solve_cycle_probe(double *tab, int64_t R, int64_t C, int64_t ld, int32_t *basis,
+                             int is_max, double tol, int rule, int64_t max_iters, int parallel,
+                             int64_t *out)
+{
+    const int64_t m = R - 1;
+    int64_t cap = 1;
+    while (cap < 4 * (max_iters + 2)) cap <<= 1;
+    uint64_t *keys = (uint64_t *)calloc((size_t)cap, sizeof(uint64_t));
+    int64_t *when = (int64_t *)malloc((size_t)cap * sizeof(int64_t));
+    if (!keys || !when) { free(keys); free(when); return -1; }
+    uint64_t h = 0;
+    for (int64_t i = 0; i < m; ++i) h += mix64(((uint64_t)i << 32) | (uint32_t)basis[i]);
+    int64_t it = 0, degenerate = 0, revisit = -1, first = -1;
+    int status = ORACLE_OPTIMAL;
+    for (;;) {
+        /* record / look up the current basis */
+        if (revisit < 0) {
+            const uint64_t key = h | 1ULL;               /* 0 marks an empty slot */
+            int64_t pos = (int64_t)(mix64(key) & (uint64_t)(cap - 1));
+            while (keys[pos] != 0 && keys[pos] != key) pos = (pos + 1) & (cap - 1);
+            if (keys[pos] == key) { revisit = it; first = when[pos]; }
+            else { keys[pos] = key; when[pos] = it; }
+        }
+        const int64_t j = oracle_find_entering_column(tab, R, C, ld, is_max, tol, rule);
+        if (j < 0) break;
+        if (max_iters > 0 && it >= max_iters) { status = ORACLE_ITERATION_LIMIT; break; }
+        const int64_t p = oracle_find_pivoting_row(tab, R, C, ld, basis, j, tol, rule);
+        if (p < 0) { status = ORACLE_UNBOUNDED; break; }
+        const double before = tab[m * ld + (C - 1)];
+        h -= mix64(((uint64_t)p << 32) | (uint32_t)basis[p]);
+        oracle_pivot(tab, R, C, ld, basis, j, p, parallel);
+        h += mix64(((uint64_t)p << 32) | (uint32_t)basis[p]);
+        if (tab[m * ld + (C - 1)] == before) ++degenerate;
+        ++it;
+    }
+    free(keys); free(when);
+    if (out) { out[0] = it; out[1] = degenerate; out[2] = revisit; out[3] = first; }
+    return status;
+}

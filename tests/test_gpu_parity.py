@@ -216,17 +216,18 @@ def test_fp_tolerance_keyword_changes_thresholds_like_the_oracle(small_path):
         assert np.array_equal(g_tab, o_tab)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 20, 21, 22, 23])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 20, 21, 22, 23, 30])
 def test_every_pivot_kernel_variant_is_bit_exact(variant):
-    """1..13: one k_iter launch per pivot, every tile shape; 20..23: the persistent cooperative
-    loop (k_persist), every tile-role variant."""
+    """1..13: one launch per pivot, every tile shape; 20..23: the persistent cooperative loop
+    (k_persist), every tile-role variant; 30: the tile staged through shared memory by the bulk
+    asynchronous copy engine (k_iter2_bulk: cp.async.bulk + mbarrier)."""
     tab, basis = random_tableau(150, 333, seed=77)     # odd C, rows not a multiple of any tile
     o_tab, o_basis = tab.copy(), basis.copy()
     ost, oit, _ = oracle.solve(o_tab, o_basis, True)
     st, res, _ = _ffi.solve(tab, basis, True, _ffi.make_opts(writeback_full=True,
                                                              pivot_variant=variant))
     assert st == ost and res.iterations == oit and np.array_equal(tab, o_tab)
-    assert res.loop_mode == (2 if variant >= 20 else 1)
+    assert res.loop_mode == (2 if 20 <= variant < 30 else 1)
 
 
 @pytest.mark.parametrize("look", ["1", "2"], ids=["round-1-look-role", "two-phase-look-role"])
@@ -448,19 +449,29 @@ def test_full_solve_is_certified_optimal_at_baseline_sizes(m, n, degenerate):
         assert abs(value - 545.8113461511593) <= 1e-8 * 545.8113461511593      # HiGHS, SURVEY 6
 
 
-@pytest.mark.parametrize("config,m,n", [("cfg2", 1024, 2048), ("cfg3", 8192, 16384)])
-def test_full_solve_end_state_equals_the_oracle_fixture(config, m, n):
-    """BASELINE configs 2 and 3 solved to the END through b200lp_solve: pivot count, the whole
-    pivot trace, final basis, RHS column and objective row equal what the oracle reaches
-    (tests/golden/<config>_final.npz, generated by tools/make_full_goldens.py -- 18 751 pivots of
-    config 3 take the CPU a quarter of an hour, so the end state travels as a fixture)."""
+@pytest.mark.parametrize("fixture,m,n", [("cfg2_final", 1024, 2048), ("cfg3_final", 8192, 16384),
+                                         ("cfg5_final", 4096, 4096), ("cfg5_rule1_final", 4096, 4096)])
+def test_full_solve_end_state_equals_the_oracle_fixture(fixture, m, n):
+    """BASELINE configs 2, 3 and 5 through b200lp_solve to where the ORACLE ends: pivot count, the
+    whole pivot trace, final basis, RHS column and objective row are equal bit for bit.
+    tests/golden/<fixture>.npz is generated by tools/make_full_goldens.py (18 751 pivots of config 3
+    take the CPU a quarter of an hour, so the end state travels as a fixture).
+      cfg2 / cfg3        the reference rule to optimality (696 / 18 751 pivots)
+      cfg5               m = n = 4096 degenerate (64 cone rows through the origin, small-integer data,
+                         exact ratio ties), the reference rule to optimality: 53 616 pivots
+      cfg5, Bland        the same LP under Bland's rule, compared at a 50 000-pivot cap -- Bland
+                         needs on the order of 10^7 pivots here, far beyond what
+                         the CPU oracle can follow"""
     import os
-    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{config}_final.npz"))
-    assert (int(fx["m"]), int(fx["n"]), int(fx["seed"]), int(fx["rule"])) == (m, n, 1234, 0)
-    tab, basis = synthetic.dense_tableau(m, n, seed=1234)
-    cap = int(fx["iterations"]) + 16
-    st, res, trace = _ffi.solve(tab, basis, True, _ffi.make_opts(trace_capacity=cap))
-    assert st == int(fx["status"]) == _ffi.OK and res.iterations == int(fx["iterations"])
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{fixture}.npz"))
+    assert (int(fx["m"]), int(fx["n"]), int(fx["seed"])) == (m, n, 1234)
+    rule, status, iters = int(fx["rule"]), int(fx["status"]), int(fx["iterations"])
+    tab, basis = synthetic.dense_tableau(m, n, seed=1234, degenerate=bool(fx["degenerate"]),
+                                         zero_frac=float(fx["zero_frac"]))
+    capped = status == _ffi.ITERATION_LIMIT
+    st, res, trace = _ffi.solve(tab, basis, True, _ffi.make_opts(
+        trace_capacity=iters + 16, pivot_rule=rule, max_iters=iters if capped else 0))
+    assert st == status and res.iterations == iters
     assert np.array_equal(np.asarray(trace, np.int32).reshape(-1, 2), fx["trace"])
     assert np.array_equal(basis, fx["basis"])
     assert np.array_equal(tab[:, -1], fx["rhs"]) and np.array_equal(tab[-1], fx["obj_row"])

@@ -213,3 +213,35 @@ def test_c_oracle_optimum_is_certified_by_duality(m, n, degenerate):
     st, _, _ = oracle.solve(tab, basis, True, max_iters=200000)
     assert st == oracle.OPTIMAL
     certify_optimal(A, b, c, tab[:, -1], tab[-1], basis)
+
+
+def test_cycle_probe_proves_beale_cycles_under_the_reference_rule_and_not_under_bland():
+    """oracle.solve_cycle_probe: a revisited basis under a deterministic rule is a proven cycle.
+    Beale's example cycles with period 6 under the reference's rule (which has no anti-cycling,
+    src/simplex.lisp:455-460); Bland's rule terminates without ever revisiting a basis."""
+    import numpy as np
+    from golden import reference_goldens as G
+    from oracle import oracle
+    g = G.BEALE
+    f64 = lambda rows: np.array([[float(x) for x in r] for r in rows], dtype=np.float64)   # noqa: E731
+    tab, basis = f64(g["matrix"]), np.array(g["basis"], np.int32)
+    st, info = oracle.solve_cycle_probe(tab.copy(), basis.copy(), True, rule=0, max_iters=300)
+    assert st == oracle.ITERATION_LIMIT and info["revisit_at"] == 6 and info["first_visit_at"] == 0
+    assert info["degenerate_pivots"] == info["pivots"] == 300
+    st, info = oracle.solve_cycle_probe(tab.copy(), basis.copy(), True, rule=1, max_iters=300)
+    assert st == oracle.OPTIMAL and info["revisit_at"] == -1
+
+
+def test_cycle_probe_on_the_degenerate_generator_stalls_but_never_cycles():
+    """Config 5's family at a size where it runs out: thousands of degenerate pivots, no basis
+    ever revisited (so the reference rule stalls on it, it does not cycle), both rules reach the
+    same optimum."""
+    from linear_programming_b200 import synthetic
+    from oracle import oracle
+    objs = []
+    for rule in (0, 1):
+        tab, basis = synthetic.dense_tableau(256, 256, degenerate=True, zero_frac=0.5)
+        st, info = oracle.solve_cycle_probe(tab, basis, True, rule=rule, max_iters=200000, parallel=True)
+        assert st == oracle.OPTIMAL and info["revisit_at"] == -1 and info["degenerate_pivots"] > 1000
+        objs.append(tab[-1, -1])
+    assert abs(objs[0] - objs[1]) <= 1e-6 * abs(objs[0])

@@ -1,7 +1,9 @@
 export B200LP_SPIN_TIMEOUT_MS=8000
-timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "variant or look or random_shapes or iteration_limit or full_size" 2>&1 | tail -5 > gpurun_out/r02_n_pytest.log
-tail -4 gpurun_out/r02_n_pytest.log
-timeout 900 python tools/loop_ab.py --shapes cfg3,slab8,cfg5 --variants 10 --iters 1000 --tag r02_n_look2 > gpurun_out/r02_n.log 2>&1
-B200LP_LOOK=1 timeout 900 python tools/loop_ab.py --shapes cfg3,slab8,cfg5 --variants 10 --iters 1000 --tag r02_n_look1 >> gpurun_out/r02_n.log 2>&1
-B200LP_LOOK_CTAS=8 timeout 900 python tools/loop_ab.py --shapes slab8 --variants 10,13,11 --iters 1000 --tag r02_n_look2_g8 >> gpurun_out/r02_n.log 2>&1
-cut -c1-330 gpurun_out/r02_n.log
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "variant or look" 2>&1 | tail -4 > gpurun_out/r02_r_pytest.log
+tail -3 gpurun_out/r02_r_pytest.log
+timeout 900 python tools/loop_ab.py --shapes cfg3,slab8,cfg5,cfg2 --variants 10,30 --iters 1000 --tag r02_r_bulk_ab > gpurun_out/r02_r.log 2>&1
+cut -c1-330 gpurun_out/r02_r.log
+B="python bench.py --steps 20 --warmup 3 --no-e2e --no-cfg4 --no-parity --no-cpu-baseline"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/r02_ncu_launches_cfg3.csv $B > gpurun_out/r02_ncu_launches.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_iter2 -s 6 -c 2 -o gpurun_out/r02_ncu_full_k_iter2_cfg3 $B > gpurun_out/r02_ncu_full.log 2>&1
+ls -la gpurun_out/*.ncu-rep; tail -2 gpurun_out/r02_ncu_full.log

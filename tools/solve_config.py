@@ -1,6 +1,6 @@
 """Full solve of one BASELINE config on the GPU through b200lp_solve, with a summary line (dev tool).
 
-usage: python tools/solve_config.py cfg5 [rule] [max_iters] [ndev]   (ndev > 1: one process, several GPUs)"""
+usage: python tools/solve_config.py cfg5 [rule] [max_iters] [ndev] [zero_frac]   (ndev > 1: one process, several GPUs)"""
 import json
 import os
 import sys
@@ -19,12 +19,13 @@ def main():
     cap = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     ndev = int(sys.argv[4]) if len(sys.argv) > 4 else 1
     m, n, deg = CONFIGS[name]
-    tab, basis = synthetic.dense_tableau(m, n, degenerate=deg)
+    zf = float(sys.argv[5]) if len(sys.argv) > 5 else 0.5
+    tab, basis = synthetic.dense_tableau(m, n, degenerate=deg, zero_frac=zf)
     t0 = time.perf_counter()
     st, res, _ = _ffi.solve(tab, basis, True, _ffi.make_opts(pivot_rule=rule, max_iters=cap,
                                                           devices=list(range(ndev))))
     wall = time.perf_counter() - t0
-    print(json.dumps(dict(config=name, m=m, n=n, rule=rule, devices_in_one_process=ndev,
+    print(json.dumps(dict(config=name, m=m, n=n, rule=rule, zero_frac=zf, devices_in_one_process=ndev,
                           exchange_mode=int(res.exchange_mode), status=st, status_text=_ffi.strerror(st),
                           pivots=int(res.iterations), objective=res.objective, wall_s=wall,
                           pivots_per_s=res.iterations / wall, ms_h2d=res.ms_h2d,
