@@ -134,8 +134,10 @@ int b200lp_solve(const b200lp_opts *opts, double *tab, int64_t R, int64_t C, int
  * phase 1 on the artificial tableau (always a `min` problem, :317-319), feasibility check,
  * zero-level artificial clean-up, coefficient copy, objective re-pricing, phase 2 on `main_tab`.
  * Both tableaus have R rows.  On return art_tab/art_basis hold the solved phase-1 tableau only
- * if opts->writeback_full; main_tab/main_basis as for b200lp_solve.  Runs on ONE GPU
- * (opts->devices[0]) even when opts->ndev > 1: the transition is order dependent over all rows. */
+ * if opts->writeback_full; main_tab/main_basis as for b200lp_solve.  With opts->ndev > 1 both
+ * tableaus are row-block sharded like b200lp_solve's; the transition's order-dependent step (the
+ * objective re-pricing over all rows in order) hands the objective row from shard to shard in
+ * rank order, so the result is bit-identical to the one-GPU run. */
 int b200lp_solve_two_phase(const b200lp_opts *opts,
                            double *art_tab, int64_t C_art, int64_t ld_art, int32_t *art_basis,
                            double *main_tab, int64_t R, int64_t C, int64_t ld, int32_t *main_basis,

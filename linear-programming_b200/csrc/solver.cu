@@ -2061,14 +2061,15 @@ int b200lp_solve_two_phase(const b200lp_opts *opts, double *art_tab, int64_t C_a
             return fail(B200LP_ERR_INTERNAL, "solve_two_phase", ex.what());
         }
     }
-    // The phase transition re-prices the objective row over ALL rows in order (:444-451), so the
-    // two-phase variant runs on one GPU: with several devices requested it uses devices[0].
-    b200lp_opts one;
-    if (opts && opts->ndev > 1) {
-        one = *opts;
-        one.ndev = 0;
-        opts = &one;
-    }
+    // Sharded (opts->ndev > 1, row blocks over the GPUs of this process): phase 1 and phase 2 are
+    // ordinary sharded solves; the transition between them is a handful of small steps:
+    //   * clean-up pivots (:419-434) are chosen on the shard that owns the row and applied with the
+    //     sharded n-pivot-row (b200lp_pivot);
+    //   * the coefficient copy (:437-441) is local to every shard;
+    //   * the objective re-pricing (:444-451) subtracts scale_i * row_i for i = 0..m-1 IN ROW ORDER
+    //     (two roundings per term): the scales come from the original objective row every shard
+    //     holds a replica of, then the row is handed from shard to shard in rank order -- each
+    //     applies its rows in order -- and the result is copied back to every replica.
     const double t0 = now_ms();
     b200lp_solver *art = nullptr, *mn = nullptr;
     b200lp_result r1, r2;
@@ -2076,17 +2077,25 @@ int b200lp_solve_two_phase(const b200lp_opts *opts, double *art_tab, int64_t C_a
     std::memset(&r2, 0, sizeof(r2));
     int64_t cleanup = 0, redundant = 0;
     int status = B200LP_OK;
-    unsigned char *d_is_basic = nullptr;
-    int *d_newcol = nullptr;
-    double *d_scales = nullptr;
+    std::vector<unsigned char *> d_is_basic;
+    std::vector<int *> d_newcol;
+    std::vector<double *> d_scales;
     auto finish = [&](int st) {
-        if (art) { cudaSetDevice(art->shards[0].device); }
-        cudaFree(d_is_basic); cudaFree(d_newcol); cudaFree(d_scales);
+        if (art) {
+            for (size_t g = 0; g < art->shards.size(); ++g) {
+                cudaSetDevice(art->shards[g].device);
+                if (g < d_is_basic.size()) cudaFree(d_is_basic[g]);
+                if (g < d_newcol.size()) cudaFree(d_newcol[g]);
+                if (g < d_scales.size()) cudaFree(d_scales[g]);
+            }
+            cudaSetDevice(art->shards[0].device);
+        }
         if (st < 0) { b200lp_destroy(art); b200lp_destroy(mn); }
         else { release(art); release(mn); }
         if (out) {
             *out = r2;
             out->status = st;
+            if (art) out->n_devices = art->world;
             out->iterations_phase1 = r1.iterations;
             out->iterations_cleanup = cleanup;
             out->redundant_rows = redundant;
@@ -2116,8 +2125,10 @@ int b200lp_solve_two_phase(const b200lp_opts *opts, double *art_tab, int64_t C_a
     const double thr_feas = art->thr_feas * feas_scale;
     if (!(std::fabs(0.0 - r1.objective) <= thr_feas)) return finish(B200LP_INFEASIBLE);
 
-    Shard &as = art->shards[0];
-    Shard &ms = mn->shards[0];
+    const size_t nsh = art->shards.size();                // both handles share the partition
+    d_is_basic.assign(nsh, nullptr);
+    d_newcol.assign(nsh, nullptr);
+    d_scales.assign(nsh, nullptr);
     std::vector<int32_t> hb((size_t)m);
 #define TP_CU(expr)                                                                     \
     do {                                                                                \
@@ -2127,32 +2138,42 @@ int b200lp_solve_two_phase(const b200lp_opts *opts, double *art_tab, int64_t C_a
             return finish(B200LP_ERR_CUDA);                                             \
         }                                                                               \
     } while (0)
-    TP_CU(cudaSetDevice(as.device));
-    TP_CU(cudaMemcpy(hb.data(), as.basis, sizeof(int32_t) * m, cudaMemcpyDeviceToHost));
+    for (Shard &as : art->shards) {
+        TP_CU(cudaSetDevice(as.device));
+        if (as.m_local > 0)
+            TP_CU(cudaMemcpy(hb.data() + as.row0, as.basis, sizeof(int32_t) * as.m_local, cudaMemcpyDeviceToHost));
+    }
     // drive zero-level artificial variables out of the basis  :419-434
     bool any_art = false;
     for (int64_t i = 0; i < m; ++i) any_art |= hb[(size_t)i] >= nv;
     if (any_art) {
-        TP_CU(cudaMalloc(&d_is_basic, (size_t)C_art));
-        TP_CU(cudaMalloc(&d_newcol, sizeof(int)));
         std::vector<unsigned char> is_basic((size_t)C_art);
         for (int64_t i = 0; i < m; ++i) {
             if (hb[(size_t)i] < nv) continue;
+            size_t g = 0;
+            while (g + 1 < nsh && i >= art->shards[g].row0 + art->shards[g].m_local) ++g;
+            Shard &as = art->shards[g];                    // the shard that owns row i
+            const int64_t li = i - as.row0;
+            TP_CU(cudaSetDevice(as.device));
+            if (!d_is_basic[g]) {
+                TP_CU(cudaMalloc(&d_is_basic[g], (size_t)C_art));
+                TP_CU(cudaMalloc(&d_newcol[g], sizeof(int)));
+            }
             double rhs = 0.0;
-            TP_CU(cudaMemcpy(&rhs, as.tab + i * as.ld + art_nv, sizeof(double), cudaMemcpyDeviceToHost));
+            TP_CU(cudaMemcpy(&rhs, as.tab + li * as.ld + art_nv, sizeof(double), cudaMemcpyDeviceToHost));
             if (ref_feas ? (rhs != 0.0) : !(std::fabs(rhs) <= thr_feas))
                 return finish(B200LP_ARTIFICIAL_NONZERO);
             std::fill(is_basic.begin(), is_basic.end(), 0);
             for (int64_t k = 0; k < m; ++k) is_basic[(size_t)hb[(size_t)k]] = 1;
-            TP_CU(cudaMemcpy(d_is_basic, is_basic.data(), (size_t)C_art, cudaMemcpyHostToDevice));
+            TP_CU(cudaMemcpy(d_is_basic[g], is_basic.data(), (size_t)C_art, cudaMemcpyHostToDevice));
             if (ref_feas)
-                k_first_nonzero_nonbasic<<<1, 1024, 0, as.stream>>>(as.tab + i * as.ld, (int)nv,
-                                                                    d_is_basic, d_newcol);
+                k_first_nonzero_nonbasic<<<1, 1024, 0, as.stream>>>(as.tab + li * as.ld, (int)nv,
+                                                                    d_is_basic[g], d_newcol[g]);
             else
-                k_largest_nonbasic<<<1, 1024, 0, as.stream>>>(as.tab + i * as.ld, (int)nv, d_is_basic,
-                                                              art->thr_pivot, d_newcol);
+                k_largest_nonbasic<<<1, 1024, 0, as.stream>>>(as.tab + li * as.ld, (int)nv, d_is_basic[g],
+                                                              art->thr_pivot, d_newcol[g]);
             int new_col = -1;
-            TP_CU(cudaMemcpyAsync(&new_col, d_newcol, sizeof(int), cudaMemcpyDeviceToHost, as.stream));
+            TP_CU(cudaMemcpyAsync(&new_col, d_newcol[g], sizeof(int), cudaMemcpyDeviceToHost, as.stream));
             TP_CU(cudaStreamSynchronize(as.stream));
             if (new_col < 0) {
                 if (ref_feas) return finish(B200LP_ARTIFICIAL_STUCK);
@@ -2164,20 +2185,49 @@ int b200lp_solve_two_phase(const b200lp_opts *opts, double *art_tab, int64_t C_a
             ++cleanup;
         }
     }
-    // copy coefficients/RHS (:437-441), basis and objective re-pricing (:444-451)
-    {
-        dim3 grid((unsigned)std::min<int64_t>((nv + 256) / 256, 64), (unsigned)std::min<int64_t>(m, 32768));
-        k_copy_art_to_main<<<grid, 256, 0, ms.stream>>>(as.tab, as.ld, (int)art_nv, ms.tab, ms.ld,
-                                                        (int)nv, (int)m);
-        TP_CU(cudaMemcpyAsync(ms.basis, as.basis, sizeof(int32_t) * m, cudaMemcpyDeviceToDevice, ms.stream));
-        TP_CU(cudaMalloc(&d_scales, sizeof(double) * m));
-        k_reprice_scales<<<(unsigned)((m + 255) / 256), 256, 0, ms.stream>>>(
-            ms.tab + m * ms.ld, ms.basis, (int)m, (int)nv, d_scales);
-        k_reprice<<<(unsigned)((nv + 1 + 127) / 128), 128, 0, ms.stream>>>(ms.tab, ms.ld, (int)m,
-                                                                          (int)nv, d_scales);
+    // copy coefficients/RHS (:437-441) and the basis, shard by shard; scales of the re-pricing from
+    // the ORIGINAL objective row (the basis columns are exact unit vectors, so the value the
+    // sequential loop of :444-451 reads for row i is the original one)
+    for (size_t g = 0; g < nsh; ++g) {
+        Shard &as = art->shards[g];
+        Shard &ms = mn->shards[g];
+        TP_CU(cudaSetDevice(ms.device));
+        TP_CU(cudaStreamSynchronize(as.stream));
+        if (ms.m_local > 0) {
+            dim3 grid((unsigned)std::min<int64_t>((nv + 256) / 256, 64), (unsigned)std::min<int64_t>(ms.m_local, 32768));
+            k_copy_art_to_main<<<grid, 256, 0, ms.stream>>>(as.tab, as.ld, (int)art_nv, ms.tab, ms.ld,
+                                                            (int)nv, ms.m_local);
+            TP_CU(cudaMemcpyAsync(ms.basis, as.basis, sizeof(int32_t) * ms.m_local, cudaMemcpyDeviceToDevice, ms.stream));
+            TP_CU(cudaMalloc(&d_scales[g], sizeof(double) * ms.m_local));
+            k_reprice_scales<<<(unsigned)((ms.m_local + 255) / 256), 256, 0, ms.stream>>>(
+                ms.tab + (int64_t)ms.m_local * ms.ld, ms.basis, ms.m_local, (int)nv, d_scales[g]);
+        }
         TP_CU(cudaStreamSynchronize(ms.stream));
         TP_CU(cudaGetLastError());
     }
+    // the objective row travels through the shards in rank order
+    for (size_t g = 0; g < nsh; ++g) {
+        Shard &ms = mn->shards[g];
+        TP_CU(cudaSetDevice(ms.device));
+        double *obj_g = ms.tab + (int64_t)ms.m_local * ms.ld;
+        if (g > 0) {
+            Shard &pv = mn->shards[g - 1];
+            TP_CU(cudaMemcpyPeer(obj_g, ms.device, pv.tab + (int64_t)pv.m_local * pv.ld, pv.device,
+                                 sizeof(double) * C));
+        }
+        if (ms.m_local > 0)
+            k_reprice<<<(unsigned)((nv + 1 + 127) / 128), 128, 0, ms.stream>>>(ms.tab, ms.ld, ms.m_local,
+                                                                              (int)nv, d_scales[g]);
+        TP_CU(cudaStreamSynchronize(ms.stream));
+        TP_CU(cudaGetLastError());
+    }
+    for (size_t g = 0; g + 1 < nsh; ++g) {                 // every replica gets the re-priced row
+        Shard &ms = mn->shards[g];
+        Shard &last = mn->shards[nsh - 1];
+        TP_CU(cudaMemcpyPeer(ms.tab + (int64_t)ms.m_local * ms.ld, ms.device,
+                             last.tab + (int64_t)last.m_local * last.ld, last.device, sizeof(double) * C));
+    }
+    TP_CU(cudaSetDevice(mn->shards[0].device));
     status = b200lp_iterate(mn, 0, &r2, nullptr, nullptr);
     if (status >= 0) {
         if (opts && opts->writeback_full) {

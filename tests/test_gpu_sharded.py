@@ -74,10 +74,70 @@ def test_eight_ranks():
     assert out.returncode == 0 and "SHARDED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
+def _two_phase_lp(seed, m, n):
+    """A random LP with <=, >= and = rows as the (art, main) tableaus build-tableau produces
+    (src/simplex.lisp:258-263, 288-325)."""
+    rng = np.random.default_rng(seed)
+    A = rng.integers(1, 9, size=(m, n)).astype(np.float64)
+    x0 = rng.integers(0, 4, size=n).astype(np.float64)
+    kinds = rng.integers(0, 3, size=m)            # 0: <=, 1: >=, 2: =
+    rhs = np.maximum(A @ x0 + np.where(kinds == 0, 5.0, np.where(kinds == 1, -3.0, 0.0)), 0.0)
+    c = rng.integers(1, 9, size=n).astype(np.float64)
+    n_slack = int((kinds != 2).sum())
+    art_rows = [i for i in range(m) if kinds[i] != 0]
+    C = n + n_slack + 1
+    main = np.zeros((m + 1, C))
+    mb = np.zeros(m, np.int32)
+    off = 0
+    for i in range(m):
+        main[i, :n] = A[i]
+        main[i, -1] = rhs[i]
+        if kinds[i] == 0:
+            main[i, n + off] = 1.0; mb[i] = n + off; off += 1
+        elif kinds[i] == 1:
+            main[i, n + off] = -1.0; mb[i] = C; off += 1
+        else:
+            mb[i] = C
+    main[m, :n] = -c
+    na = len(art_rows)
+    art = np.zeros((m + 1, C + na))
+    ab = mb.copy()
+    art[:m, :C - 1] = main[:m, :C - 1]
+    art[:m, -1] = main[:m, -1]
+    for k, row in enumerate(reversed(art_rows)):
+        art[row, C - 1 + k] = 1.0
+        ab[row] = C - 1 + k
+    art[m, :C - 1] = art[art_rows][:, :C - 1].sum(axis=0)
+    art[m, -1] = art[art_rows][:, -1].sum()
+    return art, ab, main, mb
+
+
 @needs2
-def test_two_phase_with_several_devices_requested_runs_on_the_first():
-    """b200lp_solve_two_phase is single-GPU by contract (include/b200lp.h); asking for more
-    devices must still solve, not fail."""
+@pytest.mark.parametrize("feas_mode", [0, 1], ids=["scaled", "reference"])
+@pytest.mark.parametrize("ndev,m,n,seed", [(2, 40, 30, 1), (2, 90, 60, 2), (4, 61, 45, 3), (8, 120, 80, 4),
+                                           (2, 300, 200, 5)])
+def test_sharded_two_phase_is_bit_identical_to_the_oracle(ndev, m, n, seed, feas_mode):
+    """b200lp_solve_two_phase on row-block shards (src/simplex.lisp:402-452): phase 1, the
+    clean-up pivots on the owning shard, the per-shard coefficient copy and the objective re-pricing
+    handed from shard to shard in rank order give the oracle's tableaus bit for bit."""
+    if _ngpu() < ndev:
+        pytest.skip(f"needs {ndev} GPUs")
+    art, ab, main, mb = _two_phase_lp(seed, m, n)
+    o = [x.copy() for x in (art, ab, main, mb)]
+    ost, oits = oracle.solve_two_phase(*o, True, feas_mode=feas_mode, with_redundant=True)
+    st, res = _ffi.solve_two_phase(art, ab, main, mb, True,
+                                   _ffi.make_opts(devices=list(range(ndev)), writeback_full=True,
+                                                  feas_mode=feas_mode))
+    assert st == ost and res.n_devices == ndev
+    if st in (_ffi.OK, _ffi.UNBOUNDED):
+        assert (res.iterations_phase1, res.iterations_cleanup, res.iterations, res.redundant_rows) == oits
+        assert np.array_equal(main, o[2]) and np.array_equal(mb, o[3])
+        assert np.array_equal(art, o[0]) and np.array_equal(ab, o[1])
+
+
+@needs2
+def test_two_phase_golden_on_two_devices():
+    """t/simplex.lisp:196-237 through the sharded two-phase call."""
     from golden import reference_goldens as G
     g = G.EQ_SOLVED
     b = g["initial"]
@@ -86,6 +146,7 @@ def test_two_phase_with_several_devices_requested_runs_on_the_first():
     main, mb = f64(b["main_matrix"]), np.array(b["main_basis"], np.int32)
     st, res = _ffi.solve_two_phase(art, ab, main, mb, True, _ffi.make_opts(devices=[0, 1]))
     assert st == _ffi.OK and res.objective == 28.5 and mb.tolist() == g["main_basis"]
+    assert res.n_devices == 2
 
 
 @needs2
