@@ -289,7 +289,7 @@ def run_b200(args, cfg, workload):
         from linear_programming_b200 import external_formats, simplex
         t0 = time.perf_counter()
         with open(args.mps) as f:
-            problem = external_formats.read_mps(f)
+            problem = external_formats.read_mps(f, args.mps_sense)      # an OBJSENSE record in the file wins
         t1 = time.perf_counter()
         built = simplex.build_tableau(problem, problem)
         t2 = time.perf_counter()
@@ -572,6 +572,8 @@ def main():
                     help="skip the BASELINE config 4 sub-record")
     ap.add_argument("--cfg4-steps", type=int, default=200)
     ap.add_argument("--mps", default=None, help="bench an LP read from an MPS file (single-phase LPs)")
+    ap.add_argument("--mps-sense", default="max", choices=["max", "min"],
+                    help="problem type when the file has no OBJSENSE record (read-mps's second argument)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfg = CONFIGS[args.config]

@@ -203,14 +203,30 @@ def read_mps(stream, problem_type=None, package=None, read_case="downcase", trim
         line = raw_line.rstrip("\n").rstrip(" \r")
         if not line:
             continue
+        try:
+            header, objective, problem_type, rhs_id = _mps_record(
+                line, header, objective, problem_type, rhs_id, rows, var_info, field)
+        except ParsingError:
+            raise
+        except KeyError as exc:                           # a record names a row ROWS never declared
+            raise ParsingError(f"unknown row {exc.args[0]!r} in MPS record {line!r}") from exc
+        except (ValueError, ZeroDivisionError) as exc:    # an empty or malformed numeric field
+            raise ParsingError(f"bad number in MPS record {line!r}: {exc}") from exc
+        if header == "endata":
+            break
+    return _mps_finish(rows, var_info, objective, problem_type, number_type)
+
+
+def _mps_record(line, header, objective, problem_type, rhs_id, rows, var_info, field):
+    """One line of the file; returns the updated (header, objective, problem_type, rhs_id)."""
+    if True:
         if line[0] != " ":
             card = line[:15].lower()
             if card[0] == "*":
-                continue
+                return header, objective, problem_type, rhs_id
             if card == "endata":
-                break
-            header = card.split()[0]                      # NAME carries no body records
-            continue
+                return "endata", objective, problem_type, rhs_id
+            return card.split()[0], objective, problem_type, rhs_id   # NAME carries no body records
         if header == "rows":
             kind = {"n": "objective", "g": ">=", "l": "<=", "e": "="}.get(field(1, line)[:1].lower())
             name = field(2, line, "name")
@@ -224,10 +240,14 @@ def read_mps(stream, problem_type=None, package=None, read_case="downcase", trim
             if len(field(5, line)) != 0:
                 rows[field(5, line, "name")][3].insert(0, (var, field(6, line, "number")))
         elif header == "rhs":
+            # (string= rhs-id current-rhs-id), :215-218: the caller's :rhs-id is compared as given
+            # (no case folding) with the set name as the file's read-case leaves it.  An RHS entry
+            # on the OBJECTIVE row (by MPS convention minus the objective's constant) is stored and
+            # then ignored, as in the reference (:282-285 skips the objective row).
             current = field(2, line, "name")
             if rhs_id is None:
                 rhs_id = current
-            if casefold(rhs_id) == current:
+            if rhs_id == current:
                 rows[field(3, line, "name")][1] = field(4, line, "number")
                 if len(field(5, line)) != 0:
                     rows[field(5, line, "name")][1] = field(6, line, "number")
@@ -276,6 +296,11 @@ def read_mps(stream, problem_type=None, package=None, read_case="downcase", trim
             objective = field(0, line, "name")
         else:
             raise ParsingError(f"Unknown header-card {header}")
+        return header, objective, problem_type, rhs_id
+
+
+def _mps_finish(rows, var_info, objective, problem_type, number_type):
+    """src/external-formats.lisp:282-348: rows -> constraints, single-variable rows -> bounds."""
     if problem_type not in ("max", "min"):
         raise ParsingError("No valid problem type was specified")
 
@@ -300,6 +325,8 @@ def read_mps(stream, problem_type=None, package=None, read_case="downcase", trim
             # the lower bound, respecting the coefficient's sign); the reference writes the
             # wrong slots of its (lb ub integer-p) record here
             var, coef = terms[0]
+            if coef == 0:
+                raise ParsingError(f"row with the single variable {var!r} has a zero coefficient")
             bound = Fraction(rhs) / Fraction(coef) if number_type in ("rational", Fraction) else rhs / coef
             if isinstance(bound, Fraction) and bound.denominator == 1:
                 bound = int(bound)

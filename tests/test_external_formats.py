@@ -148,6 +148,36 @@ ENDATA
         X.read_mps(text.replace(" MI bnd", " QQ bnd"), "min")
 
 
+def _mps(body):
+    return "NAME          bad\nROWS\n N  cost\n L  lim1\n" + body + "ENDATA\n"
+
+
+@pytest.mark.parametrize("body,needle", [
+    ("COLUMNS\n    x         cost               1.0   nosuch             2.0\n", "unknown row"),
+    ("COLUMNS\n    x         cost               1.0   lim1               2.x\n", "bad number"),
+    ("COLUMNS\n    x         cost               1.0   lim1               1.0\n"
+     "RHS\n    rhs       lim1                    \n", "bad number"),
+    ("COLUMNS\n    x         cost               1.0   lim1               0.0\n"
+     "RHS\n    rhs       lim1               4.0\n", "zero coefficient"),
+])
+def test_read_mps_malformed_input_raises_parsing_error_not_a_python_error(body, needle):
+    """Every malformed record ends in the reference's parsing-error (src/conditions.lisp), with the
+    offending line, never in a bare KeyError / ValueError / ZeroDivisionError."""
+    with pytest.raises(conditions.ParsingError, match=needle):
+        X.read_mps(io.StringIO(_mps(body)), "max")
+
+
+def test_read_mps_rhs_id_is_compared_as_given():
+    """(string= rhs-id current-rhs-id), src/external-formats.lisp:215-218: the set named by
+    :rhs-id is used, others are ignored; the comparison does not fold the caller's string."""
+    body = ("COLUMNS\n    x         cost               1.0   lim1               1.0\n"
+            "    y         cost               1.0   lim1               1.0\n"
+            "RHS\n    rhsa      lim1               4.0\n    rhsb      lim1               9.0\n")
+    assert X.read_mps(_mps(body), "max", rhs_id="rhsb").constraints[0][2] == 9
+    assert X.read_mps(_mps(body), "max").constraints[0][2] == 4          # default: the first set
+    assert X.read_mps(_mps(body), "max", rhs_id="RHSB").constraints[0][2] == 0   # no such set
+
+
 def test_write_standard_format():
     """t/external-formats.lisp:308-337"""
     p = P.make_linear_problem("(max (+ x y))", "(<= (+ (* 2 x) y) 5)")
