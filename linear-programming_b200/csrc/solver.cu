@@ -1372,11 +1372,20 @@ static int setup_exchange(b200lp_solver *s)
                 if (cudaDeviceCanAccessPeer(&can, a.device, b.device) != cudaSuccess || !can) {
                     ok = false; why = "no peer access between local devices"; break;
                 }
+                // enabled once per process and pair (asking again returns -- and a sanitizer
+                // reports -- cudaErrorPeerAccessAlreadyEnabled)
+                static bool enabled[kMaxDeviceLocks][kMaxDeviceLocks];
+                static std::mutex enabled_mu;
+                std::lock_guard<std::mutex> lk(enabled_mu);
+                const bool tracked = a.device >= 0 && a.device < kMaxDeviceLocks && b.device >= 0 &&
+                                     b.device < kMaxDeviceLocks;
+                if (tracked && enabled[a.device][b.device]) continue;
                 cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
                 if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
                     ok = false; why = cudaGetErrorString(e); break;
                 }
                 (void)cudaGetLastError();
+                if (tracked) enabled[a.device][b.device] = true;
             }
             if (!ok) break;
         }
