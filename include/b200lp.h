@@ -117,6 +117,8 @@ typedef struct b200lp_result {
     double  sm_clock_mhz;        /* SM clock seen by the look role (clock64 vs %globaltimer)        */
     double  ms_look_dbg[8];      /* finer split of the two phases (dev aid; see persist.cuh)        */
     int64_t redundant_rows;      /* two-phase, B200LP_FEAS_SCALED: rows left with a zero-level artificial */
+    int32_t look_cluster;        /* k_persist: thread-block cluster size of the look grid (0 = none) */
+    int32_t reserved_r;
 } b200lp_result;
 
 /* ---- one-shot calls: what the `*solver*` backend function uses ------------------------------

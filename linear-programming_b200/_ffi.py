@@ -84,6 +84,8 @@ class Result(ctypes.Structure):
         ("sm_clock_mhz", ctypes.c_double),
         ("ms_look_dbg", ctypes.c_double * 8),
         ("redundant_rows", ctypes.c_int64),
+        ("look_cluster", ctypes.c_int32),
+        ("reserved_r", ctypes.c_int32),
     ]
 
     def as_dict(self):

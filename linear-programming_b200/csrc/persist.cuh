@@ -38,6 +38,8 @@
 // Arithmetic contract as everywhere: __ddiv_rn, __dmul_rn then __dsub_rn, strict compares,
 // lowest index wins.  Bit-identical to k_iter, to the step-by-step kernels and to the oracle.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "kernels.cuh"
 
 namespace b200lp {
@@ -182,6 +184,32 @@ __device__ __forceinline__ Cand preduce(const Cand *part, int G, Cand *s_out)
     return *s_out;
 }
 
+// The look grid as ONE thread-block cluster (k_persist, one shard): the partial argmins travel
+// through distributed shared memory and the CTAs meet at the hardware cluster barrier
+// (barrier.cluster, release/acquire at cluster scope) instead of a fence + atomic + spin on a
+// global counter.  Every CTA reads all G partials from its peers' shared memory and reduces them
+// in the same order, so all agree.  `mine` is this CTA's slot; A and B phases use different slots,
+// so a slot is rewritten only after a later cluster barrier that everybody's read precedes.
+__device__ __forceinline__ Cand cluster_reduce(Cand *mine, const Cand v, const int G, Cand *s_out)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    if (threadIdx.x == 0) *mine = v;
+    cluster.sync();
+    if (threadIdx.x < 32) {
+        Cand d;
+        d.q = 0.0; d.key = 0; d.row = -1;
+        if ((int)threadIdx.x < G) {
+            const Cand *r = cluster.map_shared_rank(mine, threadIdx.x);
+            d = *r;
+        }
+        d = cand_warp_min(d);
+        if (threadIdx.x == 0) *s_out = d;
+    }
+    __syncthreads();
+    return *s_out;
+}
+
 __device__ __forceinline__ const double *p_prow(const PersistArgs &P, int slot, int w)
 {
     if (P.mode == 2) return P.xchg.peer[P.rank] + px_cand_off(slot, w, P.ld) + kCandHdr;
@@ -215,10 +243,11 @@ __device__ __forceinline__ void enter_scan(Cand &best, const double o, const int
 // ONE_STEP = false: the whole loop (k_persist).  ONE_STEP = true: decision `k_one` only (k_iter2:
 // launch L decides pivot L + 1; the previous launch is complete, so there is nothing to wait for);
 // the loop state comes from / goes back to PSync::carry.
-template <bool ONE_STEP>
+template <bool ONE_STEP, bool CLUSTER = false>
 __device__ __forceinline__ void persist_look(const PersistArgs &P, const int cta, const int G,
                                              const long long k_one)
 {
+    __shared__ Cand s_cpart[2];                            // CLUSTER: this CTA's partials (phase A, phase B)
     __shared__ Cand red[kLookThreads / 32];
     __shared__ Cand s_part;
     __shared__ int s_p, s_w;
@@ -265,10 +294,14 @@ __device__ __forceinline__ void persist_look(const PersistArgs &P, const int cta
     }
     best = cand_block_min<kLookThreads>(best, red);
     if (G > 1) {
-        if (tid == 0) S->part[1][cta] = best;
-        bar_n[1] += G;
-        if (!look_bar(S, 1, bar_n[1], P.timeout_ns)) return;
-        best = preduce(S->part[1], G, &s_part);
+        if (CLUSTER) {
+            best = cluster_reduce(&s_cpart[1], best, G, &s_part);
+        } else {
+            if (tid == 0) S->part[1][cta] = best;
+            bar_n[1] += G;
+            if (!look_bar(S, 1, bar_n[1], P.timeout_ns)) return;
+            best = preduce(S->part[1], G, &s_part);
+        }
     }
     {
         const bool accept = (best.row >= 0) && (P.rule != 0 || best.q < 0.0 - P.thr_enter);
@@ -356,10 +389,14 @@ __device__ __forceinline__ void persist_look(const PersistArgs &P, const int cta
         __syncthreads();                                           // red[] reuse
         c = cand_block_min<kLookThreads>(c, red);
         if (G > 1) {
-            if (tid == 0) S->part[0][cta] = c;
-            bar_n[0] += G;
-            if (!look_bar(S, 0, bar_n[0], P.timeout_ns)) return;
-            c = preduce(S->part[0], G, &s_part);
+            if (CLUSTER) {
+                c = cluster_reduce(&s_cpart[0], c, G, &s_part);
+            } else {
+                if (tid == 0) S->part[0][cta] = c;
+                bar_n[0] += G;
+                if (!look_bar(S, 0, bar_n[0], P.timeout_ns)) return;
+                c = preduce(S->part[0], G, &s_part);
+            }
         }
         const long long t2 = lead ? clock64() : 0ll;
         long long t3 = t2, t4 = t2;
@@ -522,10 +559,14 @@ __device__ __forceinline__ void persist_look(const PersistArgs &P, const int cta
         __syncthreads();                                           // red[] reuse
         best = cand_block_min<kLookThreads>(best, red);
         if (G > 1) {
-            if (tid == 0) S->part[1][cta] = best;
-            bar_n[1] += G;
-            if (!look_bar(S, 1, bar_n[1], P.timeout_ns)) return;
-            best = preduce(S->part[1], G, &s_part);
+            if (CLUSTER) {
+                best = cluster_reduce(&s_cpart[1], best, G, &s_part);
+            } else {
+                if (tid == 0) S->part[1][cta] = best;
+                bar_n[1] += G;
+                if (!look_bar(S, 1, bar_n[1], P.timeout_ns)) return;
+                best = preduce(S->part[1], G, &s_part);
+            }
         }
         const long long tb2 = lead ? clock64() : 0ll;
         // the scaled pivot row is complete (every look CTA passed the barrier): publish pivot k
@@ -813,6 +854,18 @@ __global__ void __launch_bounds__(kPivotThreads, 2) k_persist(const __grid_const
 {
     const int G = P.look_ctas;
     if ((int)blockIdx.x < G) persist_look<false>(P, blockIdx.x, G, 1);
+    else persist_tiles<UNROLL, STREAM>(P, (int)blockIdx.x - G, (int)gridDim.x - G);
+}
+
+// The same kernel launched with thread-block clusters of G CTAs (cooperative + cluster launch):
+// cluster 0 is the look grid and synchronises through barrier.cluster / distributed shared
+// memory; the tile CTAs sit in clusters too but never use them.  One shard only (mode 0): the
+// hardware barrier has no timeout, so it is kept away from waits on other GPUs.
+template <int UNROLL, bool STREAM>
+__global__ void __launch_bounds__(kPivotThreads, 2) k_persist_cl(const __grid_constant__ PersistArgs P)
+{
+    const int G = P.look_ctas;
+    if ((int)blockIdx.x < G) persist_look<false, true>(P, blockIdx.x, G, 1);
     else persist_tiles<UNROLL, STREAM>(P, (int)blockIdx.x - G, (int)gridDim.x - G);
 }
 

@@ -142,6 +142,7 @@ struct Shard {
     int coop = 0;               // cudaDevAttrCooperativeLaunch
     int sm_count = 0;
     int plook_ctas = 1;
+    int last_cluster = 0;       // cluster size of the last k_persist launch (0 = no clusters)
     PersistArgs pargs;          // arguments of the current b200lp_iterate call (k_iter2)
     int iter2_ctas = 0;
 };
@@ -204,9 +205,10 @@ static void shape_shard(Shard &sh)
     sh.xchg.ld = sh.ld;
     // persistent loop: one look CTA while a row is short (no look-grid barriers at all), else
     // enough that a look thread touches only a few 16-byte units per phase
-    // (measured, profiles/r02_loop_ab_*.json: 3 088-double rows 11.6 us per pivot with one look
-    // CTA, 10.2 us with four; 784-double rows 6.1 us with one, 7.7 us with four)
-    sh.plook_ctas = sh.ld <= 1536 ? 1 : sh.ld <= 8192 ? 4
+    // (measured, profiles/r02_loop_ab_*.json: 784-double rows 6.1 us per pivot with one look CTA,
+    // 6.9-7.7 us with more; 3 088-double rows 11.6 us with one, 9.5 us with eight meeting at
+    // global-memory barriers, 8.6 us with eight as one thread-block cluster)
+    sh.plook_ctas = sh.ld <= 1536 ? 1 : sh.ld <= 8192 ? 8
                   : (int)std::min<int64_t>(kPLookMax, (sh.ld + 2047) / 2048);
     if (const char *e = getenv("B200LP_LOOK_CTAS")) {
         const int g = atoi(e);
@@ -889,9 +891,56 @@ static int launch_iter2(b200lp_solver *s, Shard &sh, long long k)
     return B200LP_OK;
 }
 
+// k_persist with the look grid as one thread-block cluster (cooperative + cluster launch).  Any
+// refusal by the runtime (occupancy query, launch) falls back to the plain cooperative launch.
+template <int UNROLL, bool STREAM>
+static cudaError_t launch_persist_cluster_t(Shard &sh, PersistArgs &a, bool *launched)
+{
+    *launched = false;
+    const int G = a.look_ctas;
+    if (G < 2 || G > 8 || (G & (G - 1)) != 0) return cudaSuccess;          // portable cluster sizes
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kPivotThreads);
+    cfg.gridDim = dim3((unsigned)(G * sh.sm_count));                        // placeholder for the query
+    cfg.stream = sh.stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeCooperative;
+    attr[1].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, k_persist_cl<UNROLL, STREAM>, &cfg) != cudaSuccess ||
+        nclusters < 2) {
+        (void)cudaGetLastError();
+        return cudaSuccess;
+    }
+    cfg.gridDim = dim3((unsigned)(nclusters * G));
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_persist_cl<UNROLL, STREAM>, a);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return cudaSuccess; }
+    *launched = true;
+    return cudaSuccess;
+}
+
+static bool cluster_look_enabled()
+{
+    const char *e = getenv("B200LP_CLUSTER");            // B200LP_CLUSTER=0: global-memory barriers only
+    return !(e && e[0] == '0');
+}
+
 template <int UNROLL, bool STREAM>
 static cudaError_t launch_persist_t(Shard &sh, PersistArgs &a)
 {
+    if (a.mode == 0 && a.look_ctas > 1 && cluster_look_enabled()) {
+        bool launched = false;
+        cudaError_t e = launch_persist_cluster_t<UNROLL, STREAM>(sh, a, &launched);
+        if (e != cudaSuccess) return e;
+        sh.last_cluster = launched ? a.look_ctas : 0;
+        if (launched) return cudaSuccess;
+    } else {
+        sh.last_cluster = 0;
+    }
     static int occ = 0;                                   // CTAs per SM, same on every device here
     if (occ == 0) {
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
@@ -994,6 +1043,7 @@ static int iterate_persist(b200lp_solver *s, int64_t limit, b200lp_result *out, 
         out->exchange_mode = s->xmode;
         out->loop_mode = 2;
         out->look_ctas = s0.plook_ctas;
+        out->look_cluster = s0.last_cluster;
         out->iterations = done;
         float ms = 0.f;
         CU_TRY(cudaEventElapsedTime(&ms, s0.ev_begin, s0.ev_end));

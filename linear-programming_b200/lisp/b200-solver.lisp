@@ -54,7 +54,8 @@
   (trace-len :int32) (exchange-mode :int32) (ms-look-kernel :double) (ms-exchange :double)
   (look-kernel-launches :int64) (loop-mode :int32) (look-ctas :int32) (ms-look-wait :double)
   (ms-look-ratio :double) (ms-look-push :double) (ms-look-peer-wait :double) (ms-look-row :double)
-  (sm-clock-mhz :double) (ms-look-dbg :double :count 8) (redundant-rows :int64))
+  (sm-clock-mhz :double) (ms-look-dbg :double :count 8) (redundant-rows :int64)
+  (look-cluster :int32) (reserved-r :int32))
 
 (cffi:defcfun ("b200lp_solve" %solve) :int
   (opts :pointer) (tab :pointer) (r :int64) (c :int64) (ld :int64) (basis :pointer)

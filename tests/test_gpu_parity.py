@@ -252,6 +252,28 @@ def test_per_pivot_loop_both_look_roles_bit_exact(m, n, rule, look_ctas, look, m
     assert np.array_equal(basis, o_basis) and np.array_equal(tab, o_tab)
 
 
+@pytest.mark.parametrize("cluster", ["1", "0"], ids=["cluster-barrier", "global-barrier"])
+@pytest.mark.parametrize("look_ctas", [2, 4, 8])
+@pytest.mark.parametrize("m,n,rule", [(700, 3500, 0), (90, 5000, 1), (3000, 200, 0)])
+def test_persistent_loop_look_grid_as_a_cluster_is_bit_exact(m, n, rule, look_ctas, cluster, monkeypatch):
+    """k_persist with its look grid launched as one thread-block cluster (partial argmins through
+    distributed shared memory, barrier.cluster) and with the global-memory barriers: same bits."""
+    monkeypatch.setenv("B200LP_LOOK_CTAS", str(look_ctas))
+    monkeypatch.setenv("B200LP_CLUSTER", cluster)
+    tab, basis = random_tableau(m, n, seed=m + n, signed=True)
+    o_tab, o_basis = tab.copy(), basis.copy()
+    cap = 600
+    ost, oit, otrace = oracle.solve(o_tab, o_basis, True, rule=rule, max_iters=cap, trace_cap=cap,
+                                    parallel=True)
+    st, res, trace = _ffi.solve(tab, basis, True,
+                                _ffi.make_opts(pivot_rule=rule, max_iters=cap, trace_capacity=cap,
+                                               writeback_full=True, pivot_variant=20))
+    assert (st, res.iterations) == (ost, oit) and trace == otrace
+    assert res.loop_mode == 2 and res.look_ctas == look_ctas
+    assert res.look_cluster == (look_ctas if cluster == "1" else 0)
+    assert np.array_equal(basis, o_basis) and np.array_equal(tab, o_tab)
+
+
 @pytest.mark.parametrize("look_ctas", [1, 2, 5, 16])
 @pytest.mark.parametrize("m,n,rule", [(700, 3500, 0), (90, 5000, 1), (3000, 200, 0)])
 def test_persistent_loop_any_look_grid_is_bit_exact(m, n, rule, look_ctas, monkeypatch):

@@ -58,7 +58,7 @@ def main():
                     it = max(int(res.iterations), 1)
                     n_look = max(int(res.look_kernel_launches), 1)
                     row = dict(shape=shape, m=m, n=n, variant=v, loop_mode=int(res.loop_mode),
-                               look_ctas=int(res.look_ctas), status=int(st), pivots=it,
+                               look_ctas=int(res.look_ctas), look_cluster=int(res.look_cluster), status=int(st), pivots=it,
                                us_iter=1e3 * res.ms_solve / it,
                                gbs=16.0 * R * C * it / res.ms_solve / 1e6,
                                pivots_per_s=1e3 * it / res.ms_solve, wall_ms=1e3 * wall,
