@@ -480,6 +480,15 @@ __device__ __forceinline__ void persist_look(const PersistArgs &P, const int cta
                     }
                 }
             }
+            // the header goes out with the row; the barrier's system fence (one per CTA, after the
+            // CTA barrier) publishes both, and only the flag is stored behind it -- one membar.sys
+            // on the chain, not two
+            if (cta == 0 && tid < P.world) {
+                double *h = P.xchg.peer[tid] + px_cand_off(slot, P.rank, P.ld);
+                h[0] = c.q;
+                reinterpret_cast<long long *>(h)[1] = c.key;
+                reinterpret_cast<long long *>(h)[2] = c.row;
+            }
             if (G > 1) {                                           // every CTA's slice is on its way
                 bar_n[1] += G;
                 if (!look_bar(S, 1, bar_n[1], P.timeout_ns, /*sys=*/true)) return;
@@ -488,15 +497,9 @@ __device__ __forceinline__ void persist_look(const PersistArgs &P, const int cta
                 if (tid == 0) __threadfence_system();
                 __syncthreads();
             }
-            if (cta == 0 && tid < P.world) {
-                double *h = P.xchg.peer[tid] + px_cand_off(slot, P.rank, P.ld);
-                h[0] = c.q;
-                reinterpret_cast<long long *>(h)[1] = c.key;
-                reinterpret_cast<long long *>(h)[2] = c.row;
-                __threadfence_system();
+            if (cta == 0 && tid < P.world)
                 *reinterpret_cast<volatile unsigned long long *>(
                     P.xchg.peer[tid] + px_flag_off(slot, P.rank, P.ld)) = seq;
-            }
             t3 = lead ? clock64() : 0ll;
             // B2: ONE wait for every rank's candidate, then the same winner everywhere
             {

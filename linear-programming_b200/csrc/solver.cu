@@ -840,7 +840,8 @@ static cudaError_t launch_iter2_t(Shard &sh, long long k)
         sh.iter2_ctas = sh.pargs.look_ctas + (int)ntiles;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)sh.iter2_ctas);
+    // launch 0 only decides pivot 1: just the look CTAs, not 25 000 tile CTAs that find nothing to do
+    cfg.gridDim = dim3((unsigned)(k == 0 ? sh.pargs.look_ctas : sh.iter2_ctas));
     cfg.blockDim = dim3(kPivotThreads);
     cfg.stream = sh.stream;
     cudaLaunchAttribute attr[1];
@@ -866,7 +867,7 @@ static int launch_iter2_bulk(b200lp_solver *s, Shard &sh, long long k)
         sh.iter2_ctas = sh.pargs.look_ctas + (int)ntiles;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)sh.iter2_ctas);
+    cfg.gridDim = dim3((unsigned)(k == 0 ? sh.pargs.look_ctas : sh.iter2_ctas));
     cfg.blockDim = dim3(kPivotThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = sh.stream;
