@@ -70,6 +70,7 @@ struct alignas(128) PSync {
     alignas(128) unsigned long long look_count;
     unsigned long long ns_look, ns_wait_done, ns_a, ns_b1, ns_xwait, ns_b2;
     unsigned long long gt0, clk0, gt1, clk1;
+    unsigned int smid0, pad_smid;                 // the SM both pairs were read on (clock64 is per SM)
     unsigned long long dbg[8];                    // finer stamps of the lead thread (cycles, summed)
     alignas(128) Cand part[2][kPLookMax];
     // k_iter2 (one launch per pivot): what the look role carries from one launch to the next
@@ -275,6 +276,9 @@ __device__ __forceinline__ void persist_look(const PersistArgs &P, const int cta
         p_prev = __ldcg(&c->p_prev); w_prev = __ldcg(&c->w_prev);
     } else {
     if (lead) {
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        S->smid0 = smid;
         S->gt0 = global_timer_ns();
         S->clk0 = (unsigned long long)clock64();
     }
@@ -615,9 +619,14 @@ __device__ __forceinline__ void persist_look(const PersistArgs &P, const int cta
             S->dbg[2] += (unsigned long long)(tb1 - t4);     // phase B: loads + division + stores issued
             S->dbg[3] += (unsigned long long)(tb2 - tb1);    // phase B: reduce (+ look-grid barrier)
             S->dbg[4] += (unsigned long long)(t5 - tb2);     // publication (fence)
-            if (fin != ST_RUNNING || (ONE_STEP && (k & 63) == 0)) {
+            // second (%globaltimer, clock64) pair for the cycles -> ns conversion: clock64 is a
+            // per-SM counter, so it must come from the SM the first pair was read on (k_persist:
+            // always; k_iter2: whenever a later launch's lead CTA lands there again)
+            unsigned int smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            if (smid == S->smid0 && (fin != ST_RUNNING || ONE_STEP)) {
                 S->gt1 = global_timer_ns();
-                S->clk1 = (unsigned long long)t5;
+                S->clk1 = (unsigned long long)clock64();
             }
         }
         if (fin != ST_RUNNING || ONE_STEP) return;

@@ -208,8 +208,11 @@ static void shape_shard(Shard &sh)
     // (measured, profiles/r02_loop_ab_*.json: 784-double rows 6.1 us per pivot with one look CTA,
     // 6.9-7.7 us with more; 3 088-double rows 11.6 us with one, 9.5 us with eight meeting at
     // global-memory barriers, 8.6 us with eight as one thread-block cluster)
-    sh.plook_ctas = sh.ld <= 1536 ? 1 : sh.ld <= 8192 ? 8
-                  : (int)std::min<int64_t>(kPLookMax, (sh.ld + 2047) / 2048);
+    // Eight CTAs already give every look thread a single 16-byte unit per phase up to 4 096-double
+    // rows and a handful beyond; more CTAs only take slots from the update tiles -- sharded, the look
+    // CTAs spend most of a pivot waiting for the slowest peer's candidate.
+    sh.plook_ctas = sh.ld <= 1536 ? 1 : sh.ld <= 32768 ? 8
+                  : (int)std::min<int64_t>(kPLookMax, (sh.ld + 4095) / 4096);
     if (const char *e = getenv("B200LP_LOOK_CTAS")) {
         const int g = atoi(e);
         if (g >= 1 && g <= kPLookMax) sh.plook_ctas = g;
