@@ -2,13 +2,20 @@
 // declared in include/b200lp.h.
 //
 // Replaces the reference's n-solve-tableau (src/simplex.lisp:399-461).  The tableau lives in
-// HBM for the whole solve (two ping-pong buffers); the host only enqueues one k_iter launch per
-// iteration (every CTA returns at once when the ring slot says the solve is over) and polls a
-// Report word every `poll_interval` iterations, one batch behind the enqueue front so the GPU
-// queue never drains.  Launches use programmatic stream serialization (PDL).
+// HBM for the whole solve (two ping-pong buffers).  Three packagings of the loop, chosen by shape
+// (want_persist / small_ok below; measurements in profiles/r02_loop_ab_*.json):
+//   k_iter2   (persist.cuh)  one launch per pivot with programmatic dependent launch: look CTAs
+//             decide pivot L+1 while one CTA per 16-row tile applies pivot L.  The host enqueues
+//             launches ahead (every CTA returns at once when its decision record says the solve
+//             is over) and polls a Report word every `poll_interval` pivots, one batch behind the
+//             enqueue front, so the GPU queue never drains.  Tableaus streamed from HBM.
+//   k_persist (persist.cuh)  one cooperative kernel per b200lp_iterate call.  L2-resident tableaus.
+//   k_small   (small.cuh)    the whole solve in one CTA's shared memory.  The reference's usual sizes.
+// k_iter / k_look + k_update (kernels.cuh) are round 1's look role, kept as B200LP_LOOK=1 and as
+// the NCCL fallback.
 //
 // Sharding: contiguous row blocks (b200lp_partition), objective row replicated on every shard.
-// The per-iteration exchange of candidate pivot rows happens inside k_iter through peer-mapped
+// The per-pivot exchange of candidate pivot rows happens inside the look role through peer-mapped
 // buffers (setup_exchange: peer access in-process, CUDA IPC handles across processes); when
 // peers cannot be mapped, k_look / k_update run on two streams with an NCCL all-gather between
 // them.  A shard is one GPU: either one per process (b200lp_create_sharded, torchrun style) or
